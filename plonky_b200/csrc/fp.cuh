@@ -1,0 +1,307 @@
+// Montgomery prime-field arithmetic on 32-bit limbs for sm_100a.
+//
+// Replaces (value-for-value) src/field/monty.rs:38-177 and the inlined twins
+// src/field/bls12_377_base.rs:58-98, src/field/bls12_377_scalar.rs:53-93 of the reference: every
+// operation returns the unique fully reduced Montgomery representative in [0, p), R = 2^(32*N).
+//
+// Blackwell has no 64x64 multiplier: a "4x64-bit" field element is 8 x u32 here (12 for the
+// 377-bit base field).  The product uses two interleaved carry chains of mad.lo.cc/madc.hi.cc pairs
+// (ptxas fuses each pair into one IMAD.WIDE.U32.X, 64 lanes/clk/SM on the FMA pipe) over "even" and
+// "odd" column accumulators, with the Montgomery reduction interleaved limb by limb (CIOS).  All
+// four moduli are 1 mod 2^32, so the quotient digit is just -t0 (no multiply), and the Tweedle
+// moduli 2^254 + c have three zero limbs whose products are skipped at compile time.
+//
+// The helpers are __host__ __device__: on the host the PTX carry flag is emulated so that the SAME
+// source can be unit-tested without a GPU (tests/test_fp_host.py); the product path never runs it
+// on the host.
+#pragma once
+#include <stdint.h>
+
+#ifndef __CUDACC__
+#define __host__
+#define __device__
+#define __forceinline__ inline
+#endif
+#include "field_constants.cuh"
+
+#define PLK_HD __host__ __device__ __forceinline__
+
+namespace plk {
+// -p^-1 mod 2^32 is 0xffffffff for all four moduli (each is 1 mod 2^32).  It is deliberately read
+// from constant memory instead of being an immediate: when ptxas can see that the quotient digit is
+// just -t0 it rewrites the following mad.lo.cc/madc.hi.cc chain algebraically and no longer fuses
+// the pairs into IMAD.WIDE.U32.X (measured: 189 vs 140 FMA-pipe instructions per product).
+#ifdef __CUDACC__
+static __constant__ uint32_t kMontMu32 = 0xffffffffu;
+#endif
+namespace ptx {
+#ifdef __CUDA_ARCH__
+PLK_HD uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+PLK_HD uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+PLK_HD uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+PLK_HD uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+PLK_HD uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+PLK_HD uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+PLK_HD uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+PLK_HD uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+PLK_HD uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+PLK_HD uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+#else
+// Host emulation of the PTX condition-code register (unit tests only).
+static thread_local uint32_t CF = 0;
+PLK_HD uint32_t add_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b; CF = (uint32_t)(t >> 32); return (uint32_t)t; }
+PLK_HD uint32_t addc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b + CF; CF = (uint32_t)(t >> 32); return (uint32_t)t; }
+PLK_HD uint32_t addc(uint32_t a, uint32_t b) { return a + b + CF; }
+PLK_HD uint32_t sub_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b; CF = (uint32_t)(t >> 63); return (uint32_t)t; }
+PLK_HD uint32_t subc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b - CF; CF = (uint32_t)(t >> 63); return (uint32_t)t; }
+PLK_HD uint32_t subc(uint32_t a, uint32_t b) { return a - b - CF; }
+PLK_HD uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (uint64_t)(uint32_t)(a * b) + c; CF = (uint32_t)(t >> 32); return (uint32_t)t; }
+PLK_HD uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (uint64_t)(uint32_t)(a * b) + c + CF; CF = (uint32_t)(t >> 32); return (uint32_t)t; }
+PLK_HD uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (((uint64_t)a * b) >> 32) + c + CF; CF = (uint32_t)(t >> 32); return (uint32_t)t; }
+PLK_HD uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return (uint32_t)(((uint64_t)a * b) >> 32) + c + CF; }
+#endif
+}  // namespace ptx
+
+template <class P>
+struct Fp {
+  static constexpr int N = P::LIMBS;
+  typedef P Params;
+  uint32_t l[N];
+
+  PLK_HD static Fp zero() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < N; ++i) r.l[i] = 0;
+    return r;
+  }
+  PLK_HD static Fp one() {   // R mod p (monty.rs:36 ONE = R)
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < N; ++i) r.l[i] = P::one(i);
+    return r;
+  }
+  PLK_HD static Fp r2() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < N; ++i) r.l[i] = P::r2(i);
+    return r;
+  }
+  PLK_HD static Fp modulus() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < N; ++i) r.l[i] = P::mod(i);
+    return r;
+  }
+  PLK_HD bool is_zero() const {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) acc |= l[i];
+    return acc == 0;
+  }
+  PLK_HD bool operator==(const Fp& o) const {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) acc |= l[i] ^ o.l[i];
+    return acc == 0;
+  }
+  PLK_HD bool operator!=(const Fp& o) const { return !(*this == o); }
+
+  // r = (a >= p) ? a - p : a, for a < 2p that fits N limbs (true for every modulus here: 2p < 2^(32N)).
+  PLK_HD static Fp reduce_once(const Fp& a) {
+    Fp t;
+    t.l[0] = ptx::sub_cc(a.l[0], P::mod(0));
+#pragma unroll
+    for (int i = 1; i < N; ++i) t.l[i] = ptx::subc_cc(a.l[i], P::mod(i));
+    uint32_t borrow = ptx::subc(0, 0);   // 0 or 0xffffffff
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < N; ++i) r.l[i] = borrow ? a.l[i] : t.l[i];
+    return r;
+  }
+  // monty.rs:38-46
+  PLK_HD static Fp add(const Fp& a, const Fp& b) {
+    Fp s;
+    s.l[0] = ptx::add_cc(a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < N - 1; ++i) s.l[i] = ptx::addc_cc(a.l[i], b.l[i]);
+    s.l[N - 1] = ptx::addc(a.l[N - 1], b.l[N - 1]);
+    return reduce_once(s);
+  }
+  // monty.rs:48-56 (value: a - b mod p)
+  PLK_HD static Fp sub(const Fp& a, const Fp& b) {
+    Fp d;
+    d.l[0] = ptx::sub_cc(a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < N; ++i) d.l[i] = ptx::subc_cc(a.l[i], b.l[i]);
+    uint32_t borrow = ptx::subc(0, 0);   // all ones when a < b
+    Fp r;
+    r.l[0] = ptx::add_cc(d.l[0], P::mod(0) & borrow);
+#pragma unroll
+    for (int i = 1; i < N - 1; ++i) r.l[i] = ptx::addc_cc(d.l[i], P::mod(i) & borrow);
+    r.l[N - 1] = ptx::addc(d.l[N - 1], P::mod(N - 1) & borrow);
+    return r;
+  }
+  // monty.rs:58-64
+  PLK_HD static Fp neg(const Fp& a) {
+    Fp r;
+    r.l[0] = ptx::sub_cc(P::mod(0), a.l[0]);
+#pragma unroll
+    for (int i = 1; i < N - 1; ++i) r.l[i] = ptx::subc_cc(P::mod(i), a.l[i]);
+    r.l[N - 1] = ptx::subc(P::mod(N - 1), a.l[N - 1]);
+    bool z = a.is_zero();
+#pragma unroll
+    for (int i = 0; i < N; ++i) r.l[i] = z ? 0u : r.l[i];
+    return r;
+  }
+  PLK_HD static Fp dbl(const Fp& a) { return add(a, a); }
+
+  // One carry chain: acc[0..N-1] += (x[start], x[start+2], ...) * y, product j on columns (j, j+1).
+  // CIN: the chain continues a pending carry (CC.CF); COUT: the carry-out is added to acc[N].
+  template <bool CIN, bool COUT, int LEN>
+  PLK_HD static void mad_chain(uint32_t (&acc)[LEN], const uint32_t (&x)[N], int start, uint32_t y) {
+    acc[0] = CIN ? ptx::madc_lo_cc(x[start], y, acc[0]) : ptx::mad_lo_cc(x[start], y, acc[0]);
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+      if (j > 0) acc[j] = ptx::madc_lo_cc(x[start + j], y, acc[j]);
+      if (j + 2 < N || COUT) acc[j + 1] = ptx::madc_hi_cc(x[start + j], y, acc[j + 1]);
+      else acc[j + 1] = ptx::madc_hi(x[start + j], y, acc[j + 1]);
+    }
+    if (COUT) acc[N] = ptx::addc(acc[N], 0);
+  }
+  // Same with x = the modulus: limbs are compile-time constants, zero limbs only propagate the carry.
+  template <bool COUT, int LEN>
+  PLK_HD static void mad_chain_mod(uint32_t (&acc)[LEN], int start, uint32_t y) {
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+      const bool last = !(j + 2 < N || COUT);
+      if (P::mod(start + j) != 0) {
+        acc[j] = (j == 0) ? ptx::mad_lo_cc(P::mod(start + j), y, acc[j]) : ptx::madc_lo_cc(P::mod(start + j), y, acc[j]);
+        acc[j + 1] = last ? ptx::madc_hi(P::mod(start + j), y, acc[j + 1]) : ptx::madc_hi_cc(P::mod(start + j), y, acc[j + 1]);
+      } else {
+        acc[j] = (j == 0) ? ptx::add_cc(acc[j], 0) : ptx::addc_cc(acc[j], 0);
+        acc[j + 1] = last ? ptx::addc(acc[j + 1], 0) : ptx::addc_cc(acc[j + 1], 0);
+      }
+    }
+    if (COUT) acc[N] = ptx::addc(acc[N], 0);
+  }
+
+  // Montgomery product a*b*R^-1 mod p, interleaved limb by limb (CIOS) like monty.rs:66-107.
+  // Running value T = E + 2^32*O + pend, where E collects the 64-bit products that start on even
+  // columns and O those that start on odd columns (two independent carry chains, no carry
+  // hand-off between neighbouring products).  After each reduction step T is divided by 2^32: O
+  // becomes the new E, E >> 64 the new O, and the single limb E[1] stays "pending" on column 0;
+  // it is folded in with one add.cc whose carry enters the next odd chain (column 1).
+  // Bounds: T < 2p < 2^(32N) at step boundaries, T < 2^(32(N+1)) inside a step, hence O < 2^(32N)
+  // always (no carry out of the odd chains) and E[N] is only transiently non-zero.
+  PLK_HD static Fp mul(const Fp& a, const Fp& b) {
+    uint32_t E[N + 1], O[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { E[i] = 0; O[i] = 0; }
+    E[N] = 0;
+    uint32_t pend = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if (i == 0) {
+        mad_chain<false, false, N>(O, a.l, 1, b.l[i]);
+      } else {
+        E[0] = ptx::add_cc(E[0], pend);
+        mad_chain<true, false, N>(O, a.l, 1, b.l[i]);
+      }
+      mad_chain<false, true, N + 1>(E, a.l, 0, b.l[i]);
+      static_assert(P::MU32 == 0xffffffffu, "kMontMu32 assumes p == 1 mod 2^32");
+#ifdef __CUDA_ARCH__
+      uint32_t m = E[0] * kMontMu32;        // quotient digit
+#else
+      uint32_t m = E[0] * P::MU32;
+#endif
+      mad_chain_mod<true, N + 1>(E, 0, m);   // E[0] becomes 0
+      mad_chain_mod<false, N>(O, 1, m);
+      // T /= 2^32
+      pend = E[1];
+      uint32_t nE[N + 1], nO[N];
+#pragma unroll
+      for (int k = 0; k < N; ++k) nE[k] = O[k];
+      nE[N] = 0;
+#pragma unroll
+      for (int k = 0; k + 2 <= N; ++k) nO[k] = E[k + 2];
+      nO[N - 1] = 0;
+#pragma unroll
+      for (int k = 0; k < N; ++k) { E[k] = nE[k]; O[k] = nO[k]; }
+      E[N] = 0;
+    }
+    Fp t;
+    t.l[0] = ptx::add_cc(E[0], pend);
+#pragma unroll
+    for (int k = 1; k < N - 1; ++k) t.l[k] = ptx::addc_cc(E[k], O[k - 1]);
+    t.l[N - 1] = ptx::addc(E[N - 1], O[N - 2]);
+    return reduce_once(t);
+  }
+  PLK_HD static Fp sqr(const Fp& a) { return mul(a, a); }   // monty.rs:109-160 (same value)
+
+  PLK_HD Fp operator+(const Fp& o) const { return add(*this, o); }
+  PLK_HD Fp operator-(const Fp& o) const { return sub(*this, o); }
+  PLK_HD Fp operator*(const Fp& o) const { return mul(*this, o); }
+
+  // Montgomery form -> canonical (monty.rs:174-177 "to_monty": multiply by 1)
+  PLK_HD static Fp to_canonical(const Fp& a) {
+    Fp o = zero();
+    o.l[0] = 1;
+    return mul(a, o);
+  }
+  // canonical -> Montgomery form (monty.rs:169-172 "from_monty": multiply by R^2)
+  PLK_HD static Fp from_canonical(const Fp& c) { return mul(c, r2()); }
+
+  // a^e for a little-endian exponent of nbits bits (field.rs:309-330, same value)
+  PLK_HD static Fp pow(const Fp& a, const uint32_t* e, int nbits) {
+    Fp cur = a, prod = one();
+    for (int i = 0; i < nbits; ++i) {
+      if ((e[i >> 5] >> (i & 31)) & 1) prod = mul(prod, cur);
+      cur = sqr(cur);
+    }
+    return prod;
+  }
+  // a^-1 by Fermat (the reference uses a binary GCD, bigint_inverse.rs:6-55 + monty.rs:162-167; the
+  // inverse is unique, so the representative is identical).  a must be non-zero.
+  PLK_HD static Fp inverse(const Fp& a) {
+    uint32_t e[N];
+    // e = p - 2  (p is odd and p0 >= 3 for every modulus here? p0 = 1 -> borrow) -- do it generally
+    uint32_t borrow = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      uint64_t t = (uint64_t)P::mod(i) - (i == 0 ? 2u : 0u) - borrow;
+      e[i] = (uint32_t)t;
+      borrow = (uint32_t)(t >> 63);
+    }
+    Fp cur = a, prod = one();
+    for (int i = 0; i < P::BITS; ++i) {
+      if ((e[i >> 5] >> (i & 31)) & 1) prod = mul(prod, cur);
+      cur = sqr(cur);
+    }
+    return prod;
+  }
+};
+
+// 128-bit vectorised global/shared access of one element (32 B -> 2 x uint4, 48 B -> 3 x uint4)
+template <class F>
+__device__ __forceinline__ F load_fp(const void* base, size_t idx) {
+  F r;
+#ifdef __CUDACC__
+  const uint4* p = reinterpret_cast<const uint4*>(base) + idx * (F::N / 4);
+#pragma unroll
+  for (int i = 0; i < F::N / 4; ++i) {
+    uint4 v = p[i];
+    r.l[4 * i] = v.x; r.l[4 * i + 1] = v.y; r.l[4 * i + 2] = v.z; r.l[4 * i + 3] = v.w;
+  }
+#endif
+  return r;
+}
+template <class F>
+__device__ __forceinline__ void store_fp(void* base, size_t idx, const F& a) {
+#ifdef __CUDACC__
+  uint4* p = reinterpret_cast<uint4*>(base) + idx * (F::N / 4);
+#pragma unroll
+  for (int i = 0; i < F::N / 4; ++i) p[i] = make_uint4(a.l[4 * i], a.l[4 * i + 1], a.l[4 * i + 2], a.l[4 * i + 3]);
+#endif
+}
+
+}  // namespace plk
