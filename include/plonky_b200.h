@@ -1,0 +1,191 @@
+/* plonky_b200 -- C ABI of the B200-native MSM / NTT prover core.
+ *
+ * This is the drop-in boundary for the L1 "bulk kernel" layer of 0xPolygonZero/plonky
+ * (SURVEY.md section 8(b)).  The reference has no FFI today: the path sits behind plain generic
+ * Rust functions re-exported from the crate root (src/lib.rs:21-23).  Each entry point below
+ * names the reference function whose BODY it replaces (file:line relative to the reference root);
+ * INTEGRATION.md shows the Rust shim a maintainer would add.
+ *
+ * Data layout (all entry points)
+ *   field element : L little-endian u64 limbs in MONTGOMERY form, fully reduced, exactly the
+ *                   `limbs` array of the reference structs (src/field/tweedledee_base.rs:14-18):
+ *                   L = 4 for TweedledeeBase / TweedledumBase / Bls12377Scalar, L = 6 for Bls12377Base.
+ *   affine point  : x then y (2*L limbs)  + one u8 zero flag  (AffinePoint, src/curve/curve.rs:73-78)
+ *   projective    : x, y, z (3*L limbs)   + one u8 zero flag  (ProjectivePoint, src/curve/curve.rs:175-181;
+ *                   homogeneous: the affine point is (x/z, y/z)).
+ *   The Rust structs are not repr(C): the shim packs them into these SoA buffers, never transmutes.
+ *   `zero` arrays may be NULL on input (= no identity points).
+ *   MSM results are returned NORMALISED: z = ONE (R mod p) and (x, y) the unique affine
+ *   coordinates, or x = y = z = 0 with *zero = 1.  ProjectivePoint equality in the reference is
+ *   projective equivalence (src/curve/curve.rs:280-302), so this is a valid return value for
+ *   every caller, and it makes results bit-comparable.
+ *
+ * Errors: the reference panics on this path (assert_eq! src/curve/curve_msm.rs:67,106; log2_strict
+ *   src/util.rs:16-19; "No inverse" src/field/field.rs:267).  The C ABI never aborts: it returns a
+ *   plk_status and the shim turns non-zero into panic!.
+ *
+ * Threading: every call is re-entrant.  Host-buffer calls run on a per-calling-thread CUDA stream;
+ *   *_dev calls run on the stream the caller passes (cudaStream_t as void*).  Handles are immutable
+ *   after creation except for an internal scratch pool guarded by a mutex.
+ *
+ * Host-pointer entry points include the host<->device copies; *_dev entry points take device
+ *   pointers (cudaMalloc'ed, 16-byte aligned) and neither copy nor synchronise.
+ */
+#ifndef PLONKY_B200_H
+#define PLONKY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLK_ABI_VERSION 1
+
+typedef enum plk_status {
+  PLK_OK = 0,
+  PLK_EINVAL = 1,    /* unknown field/curve id, NULL pointer, window out of range            */
+  PLK_ELENGTH = 2,   /* scalars.len() != precomputation.len()  (curve_msm.rs:67,106)         */
+  PLK_ENOTPOW2 = 3,  /* log2_strict on a non power of two     (util.rs:16-19)                */
+  PLK_ESIZE = 4,     /* transform length != precomputation size (fft.rs:107-111)             */
+  PLK_EZERO = 5,     /* inverse of zero requested              (field.rs:267 "No inverse")   */
+  PLK_ECUDA = 6,     /* CUDA runtime error (plk_last_error_message has the text)             */
+  PLK_ENOMEM = 7,
+  PLK_ETOOBIG = 8    /* log2(n) exceeds the field's TWO_ADICITY (field.rs:430)               */
+} plk_status;
+
+/* Field::* implementors of the reference */
+enum {
+  PLK_FIELD_TWEEDLEDEE_BASE = 0, /* src/field/tweedledee_base.rs  (scalar field of Tweedledum) */
+  PLK_FIELD_TWEEDLEDUM_BASE = 1, /* src/field/tweedledum_base.rs  (scalar field of Tweedledee) */
+  PLK_FIELD_BLS12_377_SCALAR = 2, /* src/field/bls12_377_scalar.rs */
+  PLK_FIELD_BLS12_377_BASE = 3   /* src/field/bls12_377_base.rs   (6 limbs)                    */
+};
+/* Curve implementors of the reference */
+enum {
+  PLK_CURVE_TWEEDLEDEE = 0, /* src/curve/tweedledee_curve.rs: base 0, scalars 1 */
+  PLK_CURVE_TWEEDLEDUM = 1, /* src/curve/tweedledum_curve.rs: base 1, scalars 0 */
+  PLK_CURVE_BLS12_377 = 2   /* src/curve/bls12_377_curve.rs:  base 3, scalars 2 */
+};
+
+const char* plk_status_string(int status);
+const char* plk_last_error_message(void);       /* thread-local */
+int plk_abi_version(void);
+int plk_device_count(int* count);
+int plk_set_device(int device);                 /* device used by the calling thread */
+int plk_field_limbs(int field);                 /* u64 limbs per element, 0 if unknown */
+int plk_curve_base_field(int curve);
+int plk_curve_scalar_field(int curve);
+
+/* ------------------------------------------------------------------------------------------
+ * MSM  (src/curve/curve_msm.rs)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct plk_msm_table plk_msm_table;     /* = MsmPrecomputation<C> (curve_msm.rs:16-25), device resident */
+
+/* msm_precompute(generators: &[ProjectivePoint<C>], w) (curve_msm.rs:27-38).
+ * `w` is accepted for interface fidelity (1 <= w <= 32); it is a tuning knob of the reference's
+ * table layout, not semantics -- the device picks its own window for the same group element. */
+int plk_msm_precompute(int curve, const uint64_t* points_xyz, const uint8_t* zero, size_t n,
+                       unsigned w, plk_msm_table** out);
+/* same from affine generators (the form `pedersen_g` is produced in, circuit_builder.rs:1127-1133) */
+int plk_msm_precompute_affine(int curve, const uint64_t* points_xy, const uint8_t* zero, size_t n,
+                              unsigned w, plk_msm_table** out);
+size_t plk_msm_table_len(const plk_msm_table* t);
+unsigned plk_msm_table_window(const plk_msm_table* t);   /* the w the caller passed */
+void plk_msm_free(plk_msm_table* t);
+
+/* msm_execute / msm_execute_parallel(&precomputation, scalars) (curve_msm.rs:63, :102) and
+ * pedersen_hash (src/plonk_util.rs:193-198).  n must equal the table length (PLK_ELENGTH). */
+int plk_msm_execute(const plk_msm_table* t, const uint64_t* scalars, size_t n,
+                    uint64_t* out_xyz, uint8_t* out_zero);
+/* k scalar vectors against one table: the body of commit_polynomials -> coeffs_vec_to_commitments
+ * without blinding (src/plonk_util.rs:215-231, src/poly_commit.rs:52-66).  scalars is k*n*4 limbs,
+ * out_xyz k*3*L limbs, out_zero k bytes. */
+int plk_msm_execute_batch(const plk_msm_table* t, const uint64_t* scalars, size_t n, size_t k,
+                          uint64_t* out_xyz, uint8_t* out_zero);
+/* msm_parallel(scalars, generators, w) = precompute + execute (curve_msm.rs:54-61), used with
+ * changing bases by the Halo IPA (src/halo.rs:87,91,122): no table is kept. */
+int plk_msm_parallel(int curve, const uint64_t* scalars, const uint64_t* points_xyz,
+                     const uint8_t* zero, size_t n, unsigned w, uint64_t* out_xyz, uint8_t* out_zero);
+
+/* Device-resident variants.  d_scalars: n*4 u64 (Montgomery).  d_out_xyz: 3*L u64, d_out_zero: 1 byte
+ * (padded to 8).  Asynchronous on `stream`. */
+int plk_msm_execute_dev(const plk_msm_table* t, const void* d_scalars, size_t n, void* d_out_xyz,
+                        void* d_out_zero, void* stream);
+/* Multi-GPU: un-normalised partial sum (4*L u64, XYZZ coordinates) of this rank's shard ...      */
+int plk_msm_execute_partial_dev(const plk_msm_table* t, const void* d_scalars, size_t n,
+                                void* d_partial, void* stream);
+/* ... and the reduction of `count` gathered partials to one normalised point. */
+int plk_msm_combine_partials_dev(int curve, const void* d_partials, size_t count, void* d_out_xyz,
+                                 void* d_out_zero, void* stream);
+size_t plk_msm_partial_limbs(int curve);        /* u64 limbs of one partial (4*L) */
+
+/* ------------------------------------------------------------------------------------------
+ * NTT  (src/fft.rs)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct plk_fft_plan plk_fft_plan;       /* = FftPrecomputation<F> (fft.rs:28-40), device resident */
+
+/* fft_precompute(degree) (fft.rs:47-59): the plan size is 2^log2_ceil(degree). */
+int plk_fft_precompute(int field, size_t degree, plk_fft_plan** out);
+size_t plk_fft_size(const plk_fft_plan* p);     /* FftPrecomputation::size (fft.rs:36-40) */
+void plk_fft_free(plk_fft_plan* p);
+
+/* fft_with_precomputation_power_of_2(coefficients, &pre) (fft.rs:103-156): natural order in,
+ * natural order out, out[k] = sum_j c_j w^(jk), w = primitive_root_of_unity(log2 n).
+ * n must be a power of two (PLK_ENOTPOW2) equal to the plan size (PLK_ESIZE). */
+int plk_fft_pow2(const plk_fft_plan* p, const uint64_t* in, uint64_t* out, size_t n);
+/* ifft_with_precomputation_power_of_2 (fft.rs:82-101) */
+int plk_ifft_pow2(const plk_fft_plan* p, const uint64_t* in, uint64_t* out, size_t n);
+/* fft_with_precomputation (fft.rs:61-80): zero-pads n_in <= size coefficients; out has `size` elements */
+int plk_fft(const plk_fft_plan* p, const uint64_t* in, size_t n_in, uint64_t* out);
+/* k transforms of the same size (values_to_polynomials / polynomials_to_values_padded,
+ * src/plonk_util.rs:169-190): in = k rows of n_in elements, out = k rows of `size` elements;
+ * inverse != 0 selects the IFFT (then n_in must equal size). */
+int plk_fft_batch(const plk_fft_plan* p, const uint64_t* in, size_t n_in, size_t k, int inverse,
+                  uint64_t* out);
+/* Coset low-degree extension, fused: out[k] = sum_j (c_j g^j) w^(jk) over `size` points with the
+ * n_in coefficients zero-padded -- Polynomial::divide_by_z_h's first half (src/polynomial.rs:336-347)
+ * when shift == NULL (g = MULTIPLICATIVE_SUBGROUP_GENERATOR); `shift` (L limbs, Montgomery) overrides g. */
+int plk_coset_lde(const plk_fft_plan* p, const uint64_t* coeffs, size_t n_in, const uint64_t* shift,
+                  uint64_t* out);
+/* Inverse of the above: IFFT then scale coefficient i by g^-i (src/polynomial.rs:368-378). */
+int plk_coset_ifft(const plk_fft_plan* p, const uint64_t* evals, const uint64_t* shift, uint64_t* out);
+/* Polynomial::divide_by_z_h (src/polynomial.rs:330-380) for a coefficient vector of `size` elements and
+ * the vanishing polynomial X^n_gates - 1: coset LDE, pointwise * 1/(g^n w^(n i) - 1), coset IFFT,
+ * all on device. */
+int plk_divide_by_z_h(const plk_fft_plan* p, const uint64_t* coeffs, size_t n_in, size_t n_gates,
+                      uint64_t* out);
+
+/* Device-resident variants: d_in / d_out hold n_in resp. `size` elements per row, k rows.
+ * flags: bit0 inverse, bit1 coset shift by the field generator on the coefficient side. */
+#define PLK_FFT_INVERSE 1u
+#define PLK_FFT_COSET 2u
+int plk_fft_dev(const plk_fft_plan* p, const void* d_in, size_t n_in, size_t k, unsigned flags,
+                void* d_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Helpers on the same arithmetic (used by the parity tests and by callers that stay on device)
+ * ---------------------------------------------------------------------------------------- */
+/* elementwise field ops over n elements (src/field/monty.rs:38-177):
+ * 0 add, 1 sub, 2 mul, 3 square, 4 neg, 5 inverse, 6 to_canonical, 7 from_canonical, 8 double */
+int plk_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
+/* Field::batch_multiplicative_inverse (src/field/field.rs:251-278); PLK_EZERO if any input is 0 */
+int plk_batch_inverse(int field, const uint64_t* in, uint64_t* out, size_t n);
+/* ProjectivePoint::batch_to_affine (src/curve/curve.rs:216-232) */
+int plk_batch_to_affine(int curve, const uint64_t* points_xyz, const uint8_t* zero, size_t n,
+                        uint64_t* out_xy, uint8_t* out_zero);
+/* Synthetic generator set for benchmarks: P_i = [splitmix64(seed + i)] * G, affine, written to device
+ * (d_points_xy: n*2*L u64).  Stands in for blake_hash_usize_to_curve (src/hash_to_curve.rs:53-76). */
+int plk_points_generate_dev(int curve, uint64_t seed, size_t n, void* d_points_xy, void* stream);
+int plk_points_generate(int curve, uint64_t seed, size_t n, uint64_t* points_xy);
+int plk_msm_precompute_affine_dev(int curve, const void* d_points_xy, size_t n, unsigned w,
+                                  plk_msm_table** out);
+
+/* number of CUDA kernels this library has launched in the calling process (bench.py: gpu_launches) */
+uint64_t plk_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLONKY_B200_H */

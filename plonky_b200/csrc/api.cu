@@ -1,0 +1,236 @@
+// Process-wide plumbing of the C ABI (status strings, error capture, per-thread streams and scratch)
+// and the small elementwise entry points: plk_field_op, plk_batch_inverse.
+#include <mutex>
+#include "common.cuh"
+#include "fp.cuh"
+
+namespace plk {
+
+std::atomic<uint64_t> g_launches{0};
+
+static thread_local std::string t_last_error;
+void set_last_error(const std::string& s) { t_last_error = s; }
+
+struct ThreadCtx {
+  cudaStream_t stream = nullptr;
+  int device = -1;
+  DevBuf scratch[8];
+  ~ThreadCtx() {
+    // the CUDA context may already be gone at thread/process teardown: never throw from here
+    for (auto& b : scratch) { if (b.p) { cudaFree(b.p); b.p = nullptr; } }
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+static thread_local ThreadCtx t_ctx;
+
+static void ensure_ctx() {
+  int dev = 0;
+  PLK_CUDA(cudaGetDevice(&dev));
+  if (t_ctx.stream && t_ctx.device == dev) return;
+  if (t_ctx.stream) {
+    for (auto& b : t_ctx.scratch) b.release();
+    cudaStreamDestroy(t_ctx.stream);
+    t_ctx.stream = nullptr;
+  }
+  PLK_CUDA(cudaStreamCreateWithFlags(&t_ctx.stream, cudaStreamNonBlocking));
+  t_ctx.device = dev;
+}
+cudaStream_t thread_stream() {
+  ensure_ctx();
+  return t_ctx.stream;
+}
+void* thread_scratch(int slot, size_t bytes) {
+  ensure_ctx();
+  if (slot < 0 || slot >= 8) fail(PLK_EINVAL, "bad scratch slot");
+  DevBuf& b = t_ctx.scratch[slot];
+  if (bytes > b.bytes) {
+    // growing: nothing on this thread's stream may still use the old block
+    if (b.p) PLK_CUDA(cudaStreamSynchronize(t_ctx.stream));
+    b.alloc(bytes + bytes / 8);
+  }
+  return b.p;
+}
+
+// ---- elementwise kernels ----------------------------------------------------------------------
+template <class P>
+__global__ void field_op_kernel(int op, const void* a, const void* b, void* out, unsigned long long n) {
+  typedef Fp<P> F;
+  unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  F x = load_fp<F>(a, i), y = b ? load_fp<F>(b, i) : F::zero(), r;
+  switch (op) {
+    case 0: r = F::add(x, y); break;
+    case 1: r = F::sub(x, y); break;
+    case 2: r = F::mul(x, y); break;
+    case 3: r = F::sqr(x); break;
+    case 4: r = F::neg(x); break;
+    case 5: r = F::inverse(x); break;
+    case 6: r = F::to_canonical(x); break;
+    case 7: r = F::from_canonical(x); break;
+    default: r = F::dbl(x); break;
+  }
+  store_fp<F>(out, i, r);
+}
+
+// Montgomery's trick (field.rs:251-278) per thread over a strip of `strip` consecutive elements:
+// prefix products, one inversion, back substitution.  zero_flag is set if any input is zero.
+template <class P>
+__global__ void batch_inverse_kernel(const void* in, void* out, unsigned long long n, unsigned strip, int* zero_flag) {
+  typedef Fp<P> F;
+  unsigned long long t = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  unsigned long long lo = t * strip;
+  if (lo >= n) return;
+  unsigned long long hi = lo + strip < n ? lo + strip : n;
+  F acc = F::one();
+  for (unsigned long long i = lo; i < hi; ++i) {
+    F x = load_fp<F>(in, i);
+    if (x.is_zero()) { *zero_flag = 1; return; }
+    store_fp<F>(out, i, acc);          // prefix product of the elements before i
+    acc = F::mul(acc, x);
+  }
+  F inv = F::inverse(acc);
+  for (unsigned long long i = hi; i-- > lo;) {
+    F x = load_fp<F>(in, i);
+    F pre = load_fp<F>(out, i);
+    store_fp<F>(out, i, F::mul(inv, pre));
+    inv = F::mul(inv, x);
+  }
+}
+
+template <class P>
+void launch_field_op(int op, const void* a, const void* b, void* out, size_t n, cudaStream_t st) {
+  if (n == 0) return;
+  field_op_kernel<P><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(op, a, b, out, n);
+  PLK_LAUNCHED();
+}
+template <class P>
+void launch_batch_inverse(const void* in, void* out, size_t n, int* d_flag, cudaStream_t st) {
+  if (n == 0) return;
+  const unsigned strip = n >= (1u << 16) ? 16 : 4;
+  const size_t threads = (n + strip - 1) / strip;
+  batch_inverse_kernel<P><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(in, out, n, strip, d_flag);
+  PLK_LAUNCHED();
+}
+
+}  // namespace plk
+
+using namespace plk;
+
+#define PLK_FIELD_DISPATCH(field, FN, ...)                                         \
+  switch (field) {                                                                 \
+    case PLK_FIELD_TWEEDLEDEE_BASE: FN<TweedledeeBaseParams>(__VA_ARGS__); break;  \
+    case PLK_FIELD_TWEEDLEDUM_BASE: FN<TweedledumBaseParams>(__VA_ARGS__); break;  \
+    case PLK_FIELD_BLS12_377_SCALAR: FN<Bls12377ScalarParams>(__VA_ARGS__); break; \
+    case PLK_FIELD_BLS12_377_BASE: FN<Bls12377BaseParams>(__VA_ARGS__); break;     \
+    default: fail(PLK_EINVAL, "unknown field id");                                 \
+  }
+
+void plk_launch_field_inverse(int field, const void* d_in, void* d_out, size_t n, cudaStream_t st) {
+  PLK_FIELD_DISPATCH(field, launch_field_op, 5, d_in, nullptr, d_out, n, st);
+}
+
+extern "C" {
+
+const char* plk_status_string(int status) {
+  switch (status) {
+    case PLK_OK: return "ok";
+    case PLK_EINVAL: return "invalid argument";
+    case PLK_ELENGTH: return "precomputation / scalars length mismatch";
+    case PLK_ENOTPOW2: return "Not a power of two";
+    case PLK_ESIZE: return "length does not match the precomputation size";
+    case PLK_EZERO: return "No inverse";
+    case PLK_ECUDA: return "CUDA error";
+    case PLK_ENOMEM: return "out of memory";
+    case PLK_ETOOBIG: return "size exceeds the field's two-adicity";
+  }
+  return "unknown status";
+}
+const char* plk_last_error_message(void) { return t_last_error.c_str(); }
+int plk_abi_version(void) { return PLK_ABI_VERSION; }
+int plk_device_count(int* count) {
+  return guarded([&] {
+    if (!count) fail(PLK_EINVAL, "NULL count");
+    PLK_CUDA(cudaGetDeviceCount(count));
+  });
+}
+int plk_set_device(int device) {
+  return guarded([&] { PLK_CUDA(cudaSetDevice(device)); });
+}
+int plk_field_limbs(int field) {
+  switch (field) {
+    case PLK_FIELD_TWEEDLEDEE_BASE:
+    case PLK_FIELD_TWEEDLEDUM_BASE:
+    case PLK_FIELD_BLS12_377_SCALAR: return 4;
+    case PLK_FIELD_BLS12_377_BASE: return 6;
+  }
+  return 0;
+}
+int plk_curve_base_field(int curve) {
+  switch (curve) {
+    case PLK_CURVE_TWEEDLEDEE: return PLK_FIELD_TWEEDLEDEE_BASE;
+    case PLK_CURVE_TWEEDLEDUM: return PLK_FIELD_TWEEDLEDUM_BASE;
+    case PLK_CURVE_BLS12_377: return PLK_FIELD_BLS12_377_BASE;
+  }
+  return -1;
+}
+int plk_curve_scalar_field(int curve) {
+  switch (curve) {
+    case PLK_CURVE_TWEEDLEDEE: return PLK_FIELD_TWEEDLEDUM_BASE;
+    case PLK_CURVE_TWEEDLEDUM: return PLK_FIELD_TWEEDLEDEE_BASE;
+    case PLK_CURVE_BLS12_377: return PLK_FIELD_BLS12_377_SCALAR;
+  }
+  return -1;
+}
+uint64_t plk_kernel_launch_count(void) { return g_launches.load(); }
+
+int plk_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+  return guarded([&] {
+    const int L = plk_field_limbs(field);
+    if (!L) fail(PLK_EINVAL, "unknown field id");
+    if (op < 0 || op > 8) fail(PLK_EINVAL, "unknown op");
+    if (n == 0) return;
+    if (!a || !out || ((op <= 2) && !b)) fail(PLK_EINVAL, "NULL buffer");
+    cudaStream_t st = thread_stream();
+    const size_t bytes = n * L * 8;
+    void* da = thread_scratch(0, bytes);
+    void* db = thread_scratch(1, bytes);
+    void* dout = thread_scratch(2, bytes);
+    PLK_CUDA(cudaMemcpyAsync(da, a, bytes, cudaMemcpyHostToDevice, st));
+    if (b) PLK_CUDA(cudaMemcpyAsync(db, b, bytes, cudaMemcpyHostToDevice, st));
+    if (op == 5) {
+      // inverse of zero is an error in the reference (field.rs:159-165 returns None, Div panics)
+      for (size_t i = 0; i < n; ++i) {
+        bool z = true;
+        for (int j = 0; j < L; ++j) z = z && a[i * L + j] == 0;
+        if (z) fail(PLK_EZERO, "No inverse");
+      }
+    }
+    PLK_FIELD_DISPATCH(field, launch_field_op, op, da, b ? db : nullptr, dout, n, st);
+    PLK_CUDA(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, st));
+    PLK_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+int plk_batch_inverse(int field, const uint64_t* in, uint64_t* out, size_t n) {
+  return guarded([&] {
+    const int L = plk_field_limbs(field);
+    if (!L) fail(PLK_EINVAL, "unknown field id");
+    if (n == 0) return;
+    if (!in || !out) fail(PLK_EINVAL, "NULL buffer");
+    cudaStream_t st = thread_stream();
+    const size_t bytes = n * L * 8;
+    void* din = thread_scratch(0, bytes);
+    void* dout = thread_scratch(1, bytes);
+    int* dflag = reinterpret_cast<int*>(thread_scratch(2, 16));
+    PLK_CUDA(cudaMemcpyAsync(din, in, bytes, cudaMemcpyHostToDevice, st));
+    PLK_CUDA(cudaMemsetAsync(dflag, 0, sizeof(int), st));
+    PLK_FIELD_DISPATCH(field, launch_batch_inverse, din, dout, n, dflag, st);
+    int flag = 0;
+    PLK_CUDA(cudaMemcpyAsync(&flag, dflag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PLK_CUDA(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, st));
+    PLK_CUDA(cudaStreamSynchronize(st));
+    if (flag) fail(PLK_EZERO, "No inverse");      // field.rs:267
+  });
+}
+
+}  // extern "C"
