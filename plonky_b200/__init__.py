@@ -1,0 +1,406 @@
+"""plonky_b200 -- host-side mirror of plonky's L1 "bulk kernel" surface over the sm_100a C ABI.
+
+The reference (0xPolygonZero/plonky) is Rust; its toolchain is not available in this image, so the
+host side above the C ABI (include/plonky_b200.h) is mirrored here with the SAME function names,
+argument meaning and error behaviour as the reference functions it fronts:
+
+    msm_precompute / msm_execute / msm_execute_parallel / msm_parallel   src/curve/curve_msm.rs:27-157
+    pedersen_hash                                                        src/plonk_util.rs:193-198
+    fft_precompute / fft / fft_with_precomputation /
+    fft_with_precomputation_power_of_2 / ifft_with_precomputation_power_of_2   src/fft.rs:42-156
+    coset_lde / coset_ifft / divide_by_z_h                               src/polynomial.rs:330-380
+
+Data: numpy uint64 arrays of little-endian limbs in Montgomery form (exactly the reference's `limbs`):
+field vectors (n, L); projective points (n, 3, L) + uint8 zero flags; affine points (n, 2, L) + flags.
+Panics of the reference (assert_eq!, log2_strict, "No inverse") surface as PlonkyPanic.
+
+There is NO CPU fallback: importing works without a GPU (so the ABI can be inspected), but every
+compute call goes to libplonky_b200.so and fails loudly if the library or a CUDA device is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+
+__all__ = [
+    "PlonkyPanic", "CudaError", "lib", "library_path",
+    "TWEEDLEDEE_BASE", "TWEEDLEDUM_BASE", "BLS12_377_SCALAR", "BLS12_377_BASE",
+    "TWEEDLEDEE", "TWEEDLEDUM", "BLS12_377",
+    "MsmPrecomputation", "msm_precompute", "msm_precompute_affine", "msm_execute", "msm_execute_parallel",
+    "msm_execute_batch", "msm_parallel", "pedersen_hash",
+    "FftPrecomputation", "fft_precompute", "fft", "fft_with_precomputation", "fft_with_precomputation_power_of_2",
+    "ifft_with_precomputation_power_of_2", "fft_batch", "coset_lde", "coset_ifft", "divide_by_z_h",
+    "field_op", "batch_multiplicative_inverse", "batch_to_affine", "points_generate", "kernel_launch_count",
+]
+
+# ids of include/plonky_b200.h
+TWEEDLEDEE_BASE, TWEEDLEDUM_BASE, BLS12_377_SCALAR, BLS12_377_BASE = 0, 1, 2, 3
+TWEEDLEDEE, TWEEDLEDUM, BLS12_377 = 0, 1, 2
+FIELD_LIMBS = {0: 4, 1: 4, 2: 4, 3: 6}
+CURVE_BASE_FIELD = {0: 0, 1: 1, 2: 3}
+CURVE_SCALAR_FIELD = {0: 1, 1: 0, 2: 2}
+
+PLK_OK, PLK_EINVAL, PLK_ELENGTH, PLK_ENOTPOW2, PLK_ESIZE, PLK_EZERO, PLK_ECUDA, PLK_ENOMEM, PLK_ETOOBIG = range(9)
+
+
+class PlonkyPanic(AssertionError):
+    """The reference panics here (assert_eq!, log2_strict, expect("No inverse"))."""
+
+
+class CudaError(RuntimeError):
+    pass
+
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "libplonky_b200.so")
+
+
+def lib():
+    """Load libplonky_b200.so (built in-tree by __graft_entry__.build() / plonky_b200/csrc/Makefile)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise CudaError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU fallback)")
+    L = C.CDLL(path)
+    vp, u64p, u8p, sz = C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint8), C.c_size_t
+    L.plk_status_string.restype = C.c_char_p
+    L.plk_status_string.argtypes = [C.c_int]
+    L.plk_last_error_message.restype = C.c_char_p
+    L.plk_abi_version.restype = C.c_int
+    L.plk_device_count.argtypes = [C.POINTER(C.c_int)]
+    L.plk_set_device.argtypes = [C.c_int]
+    L.plk_msm_precompute.argtypes = [C.c_int, u64p, u8p, sz, C.c_uint, C.POINTER(vp)]
+    L.plk_msm_precompute_affine.argtypes = [C.c_int, u64p, u8p, sz, C.c_uint, C.POINTER(vp)]
+    L.plk_msm_precompute_affine_dev.argtypes = [C.c_int, vp, sz, C.c_uint, C.POINTER(vp)]
+    L.plk_msm_table_len.argtypes = [vp]
+    L.plk_msm_table_len.restype = sz
+    L.plk_msm_table_window.argtypes = [vp]
+    L.plk_msm_table_window.restype = C.c_uint
+    L.plk_msm_free.argtypes = [vp]
+    L.plk_msm_free.restype = None
+    L.plk_msm_execute.argtypes = [vp, u64p, sz, u64p, u8p]
+    L.plk_msm_execute_batch.argtypes = [vp, u64p, sz, sz, u64p, u8p]
+    L.plk_msm_parallel.argtypes = [C.c_int, u64p, u64p, u8p, sz, C.c_uint, u64p, u8p]
+    L.plk_msm_execute_dev.argtypes = [vp, vp, sz, vp, vp, vp]
+    L.plk_msm_execute_partial_dev.argtypes = [vp, vp, sz, vp, vp]
+    L.plk_msm_combine_partials_dev.argtypes = [C.c_int, vp, sz, vp, vp, vp]
+    L.plk_msm_partial_limbs.argtypes = [C.c_int]
+    L.plk_msm_partial_limbs.restype = sz
+    L.plk_fft_precompute.argtypes = [C.c_int, sz, C.POINTER(vp)]
+    L.plk_fft_size.argtypes = [vp]
+    L.plk_fft_size.restype = sz
+    L.plk_fft_free.argtypes = [vp]
+    L.plk_fft_free.restype = None
+    L.plk_fft_pow2.argtypes = [vp, u64p, u64p, sz]
+    L.plk_ifft_pow2.argtypes = [vp, u64p, u64p, sz]
+    L.plk_fft.argtypes = [vp, u64p, sz, u64p]
+    L.plk_fft_batch.argtypes = [vp, u64p, sz, sz, C.c_int, u64p]
+    L.plk_coset_lde.argtypes = [vp, u64p, sz, u64p, u64p]
+    L.plk_coset_ifft.argtypes = [vp, u64p, u64p, u64p]
+    L.plk_divide_by_z_h.argtypes = [vp, u64p, sz, sz, u64p]
+    L.plk_fft_dev.argtypes = [vp, vp, sz, sz, C.c_uint, vp, vp]
+    L.plk_field_op.argtypes = [C.c_int, C.c_int, u64p, u64p, u64p, sz]
+    L.plk_batch_inverse.argtypes = [C.c_int, u64p, u64p, sz]
+    L.plk_batch_to_affine.argtypes = [C.c_int, u64p, u8p, sz, u64p, u8p]
+    L.plk_points_generate_dev.argtypes = [C.c_int, C.c_uint64, sz, vp, vp]
+    L.plk_points_generate.argtypes = [C.c_int, C.c_uint64, sz, u64p]
+    L.plk_kernel_launch_count.restype = C.c_uint64
+    _LIB = L
+    return L
+
+
+def _check(status: int):
+    if status == PLK_OK:
+        return
+    L = lib()
+    msg = (L.plk_last_error_message() or b"").decode() or L.plk_status_string(status).decode()
+    if status in (PLK_ELENGTH, PLK_ENOTPOW2, PLK_ESIZE, PLK_EZERO, PLK_ETOOBIG):
+        raise PlonkyPanic(msg)
+    if status == PLK_EINVAL:
+        raise ValueError(msg)
+    raise CudaError(msg)
+
+
+def _u64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+def _p64(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint64))
+
+
+def _p8(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8)) if a is not None else None
+
+
+def _zero_flags(zero, n) -> Optional[np.ndarray]:
+    if zero is None:
+        return None
+    z = np.ascontiguousarray(zero, dtype=np.uint8)
+    assert z.shape == (n,)
+    return z
+
+
+def kernel_launch_count() -> int:
+    return int(lib().plk_kernel_launch_count())
+
+
+# ------------------------------------------------------------------------------------------------
+# MSM (src/curve/curve_msm.rs)
+# ------------------------------------------------------------------------------------------------
+class MsmPrecomputation:
+    """MsmPrecomputation<C> (curve_msm.rs:16-25): here a device-resident table behind an opaque handle.
+    Keeps (curve, generators, w) so that it stays clonable / serialisable like the reference struct."""
+
+    def __init__(self, curve: int, handle, n: int, w: int, generators=None, zero=None, affine=False):
+        self.curve, self.handle, self.n, self.w = curve, handle, n, w
+        self.generators, self.zero, self.affine = generators, zero, affine
+
+    def __len__(self):
+        return self.n
+
+    def close(self):
+        if self.handle:
+            lib().plk_msm_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def msm_precompute(curve: int, generators, w: int, zero=None, keep_host_copy: bool = False) -> MsmPrecomputation:
+    """msm_precompute(generators: &[ProjectivePoint<C>], w) (curve_msm.rs:27-38).
+    generators: (n, 3, L) projective Montgomery limbs, zero: optional (n,) flags."""
+    Lb = FIELD_LIMBS[CURVE_BASE_FIELD[curve]]
+    g = _u64(generators).reshape(-1, 3, Lb)
+    n = g.shape[0]
+    z = _zero_flags(zero, n)
+    h = C.c_void_p()
+    _check(lib().plk_msm_precompute(curve, _p64(g), _p8(z), n, w, C.byref(h)))
+    return MsmPrecomputation(curve, h, n, w, g if keep_host_copy else None, z if keep_host_copy else None)
+
+
+def msm_precompute_affine(curve: int, generators_xy, w: int, zero=None) -> MsmPrecomputation:
+    Lb = FIELD_LIMBS[CURVE_BASE_FIELD[curve]]
+    g = _u64(generators_xy).reshape(-1, 2, Lb)
+    n = g.shape[0]
+    z = _zero_flags(zero, n)
+    h = C.c_void_p()
+    _check(lib().plk_msm_precompute_affine(curve, _p64(g), _p8(z), n, w, C.byref(h)))
+    return MsmPrecomputation(curve, h, n, w, affine=True)
+
+
+def msm_execute(precomputation: MsmPrecomputation, scalars) -> Tuple[np.ndarray, bool]:
+    """msm_execute(&precomputation, scalars) (curve_msm.rs:63-100).  Returns the ProjectivePoint as
+    ((3, L) limbs x, y, z with z = ONE, zero flag)."""
+    Lb = FIELD_LIMBS[CURVE_BASE_FIELD[precomputation.curve]]
+    s = _u64(scalars).reshape(-1, 4)
+    out = np.zeros((3, Lb), dtype=np.uint64)
+    oz = np.zeros(1, dtype=np.uint8)
+    _check(lib().plk_msm_execute(precomputation.handle, _p64(s), s.shape[0], _p64(out), _p8(oz)))
+    return out, bool(oz[0])
+
+
+def msm_execute_parallel(precomputation: MsmPrecomputation, scalars):
+    """msm_execute_parallel (curve_msm.rs:102-157): same value as msm_execute."""
+    return msm_execute(precomputation, scalars)
+
+
+def pedersen_hash(xs, pedersen_g_msm_precomputation: MsmPrecomputation):
+    """pedersen_hash(xs, &precomputation) (src/plonk_util.rs:193-198)."""
+    return msm_execute_parallel(pedersen_g_msm_precomputation, xs)
+
+
+def msm_execute_batch(precomputation: MsmPrecomputation, scalars_k):
+    """k scalar vectors against one table (commit_polynomials, src/plonk_util.rs:215-231)."""
+    Lb = FIELD_LIMBS[CURVE_BASE_FIELD[precomputation.curve]]
+    s = _u64(scalars_k)
+    k, n = s.shape[0], s.shape[1]
+    s = s.reshape(k, n, 4)
+    out = np.zeros((k, 3, Lb), dtype=np.uint64)
+    oz = np.zeros(k, dtype=np.uint8)
+    _check(lib().plk_msm_execute_batch(precomputation.handle, _p64(s), n, k, _p64(out), _p8(oz)))
+    return out, oz.astype(bool)
+
+
+def msm_parallel(curve: int, scalars, generators, w: int, zero=None):
+    """msm_parallel(scalars, generators, w) (curve_msm.rs:54-61)."""
+    Lb = FIELD_LIMBS[CURVE_BASE_FIELD[curve]]
+    s = _u64(scalars).reshape(-1, 4)
+    g = _u64(generators).reshape(-1, 3, Lb)
+    if g.shape[0] != s.shape[0]:
+        raise PlonkyPanic("precomputation / scalars length mismatch")
+    z = _zero_flags(zero, g.shape[0])
+    out = np.zeros((3, Lb), dtype=np.uint64)
+    oz = np.zeros(1, dtype=np.uint8)
+    _check(lib().plk_msm_parallel(curve, _p64(s), _p64(g), _p8(z), s.shape[0], w, _p64(out), _p8(oz)))
+    return out, bool(oz[0])
+
+
+# ------------------------------------------------------------------------------------------------
+# NTT (src/fft.rs)
+# ------------------------------------------------------------------------------------------------
+class FftPrecomputation:
+    """FftPrecomputation<F> (fft.rs:28-40): device-resident twiddle tables behind an opaque handle;
+    reconstructible from (field, degree)."""
+
+    def __init__(self, field: int, degree: int, handle):
+        self.field, self.degree, self.handle = field, degree, handle
+
+    def size(self) -> int:
+        return int(lib().plk_fft_size(self.handle))
+
+    def close(self):
+        if self.handle:
+            lib().plk_fft_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def fft_precompute(field: int, degree: int) -> FftPrecomputation:
+    """fft_precompute(degree) (fft.rs:47-59)."""
+    h = C.c_void_p()
+    _check(lib().plk_fft_precompute(field, degree, C.byref(h)))
+    return FftPrecomputation(field, degree, h)
+
+
+def fft_with_precomputation_power_of_2(coefficients, precomputation: FftPrecomputation) -> np.ndarray:
+    """fft.rs:103-156."""
+    L = FIELD_LIMBS[precomputation.field]
+    a = _u64(coefficients).reshape(-1, L)
+    out = np.empty_like(a)
+    _check(lib().plk_fft_pow2(precomputation.handle, _p64(a), _p64(out), a.shape[0]))
+    return out
+
+
+def ifft_with_precomputation_power_of_2(points, precomputation: FftPrecomputation) -> np.ndarray:
+    """fft.rs:82-101."""
+    L = FIELD_LIMBS[precomputation.field]
+    a = _u64(points).reshape(-1, L)
+    out = np.empty_like(a)
+    _check(lib().plk_ifft_pow2(precomputation.handle, _p64(a), _p64(out), a.shape[0]))
+    return out
+
+
+def fft_with_precomputation(coefficients, precomputation: FftPrecomputation) -> np.ndarray:
+    """fft.rs:61-80: zero-pad to the next power of two."""
+    L = FIELD_LIMBS[precomputation.field]
+    a = _u64(coefficients).reshape(-1, L)
+    out = np.empty((precomputation.size(), L), dtype=np.uint64)
+    _check(lib().plk_fft(precomputation.handle, _p64(a), a.shape[0], _p64(out)))
+    return out
+
+
+def fft(field: int, coefficients) -> np.ndarray:
+    """fft(coefficients) (fft.rs:42-45)."""
+    L = FIELD_LIMBS[field]
+    a = _u64(coefficients).reshape(-1, L)
+    pre = fft_precompute(field, a.shape[0])
+    try:
+        return fft_with_precomputation(a, pre)
+    finally:
+        pre.close()
+
+
+def fft_batch(rows, precomputation: FftPrecomputation, inverse: bool = False) -> np.ndarray:
+    """values_to_polynomials / polynomials_to_values_padded (src/plonk_util.rs:169-190): k rows at once;
+    forward rows shorter than the plan size are zero-padded."""
+    L = FIELD_LIMBS[precomputation.field]
+    a = _u64(rows)
+    k, n_in = a.shape[0], a.shape[1]
+    out = np.empty((k, precomputation.size(), L), dtype=np.uint64)
+    _check(lib().plk_fft_batch(precomputation.handle, _p64(a), n_in, k, 1 if inverse else 0, _p64(out)))
+    return out
+
+
+def coset_lde(coefficients, precomputation: FftPrecomputation, shift=None) -> np.ndarray:
+    """c_i * g^i, zero-pad, FFT (src/polynomial.rs:336-347); shift=None uses MULTIPLICATIVE_SUBGROUP_GENERATOR."""
+    L = FIELD_LIMBS[precomputation.field]
+    a = _u64(coefficients).reshape(-1, L)
+    out = np.empty((precomputation.size(), L), dtype=np.uint64)
+    sp = _p64(_u64(shift)) if shift is not None else None
+    _check(lib().plk_coset_lde(precomputation.handle, _p64(a), a.shape[0], sp, _p64(out)))
+    return out
+
+
+def coset_ifft(evaluations, precomputation: FftPrecomputation, shift=None) -> np.ndarray:
+    """IFFT then scale coefficient i by g^-i (src/polynomial.rs:368-378)."""
+    L = FIELD_LIMBS[precomputation.field]
+    a = _u64(evaluations).reshape(-1, L)
+    if a.shape[0] != precomputation.size():
+        raise PlonkyPanic("Number of points does not match size of subgroup in precomputation")
+    out = np.empty_like(a)
+    sp = _p64(_u64(shift)) if shift is not None else None
+    _check(lib().plk_coset_ifft(precomputation.handle, _p64(a), sp, _p64(out)))
+    return out
+
+
+def divide_by_z_h(coefficients, n_gates: int, precomputation: FftPrecomputation) -> np.ndarray:
+    """Polynomial::divide_by_z_h (src/polynomial.rs:330-380)."""
+    L = FIELD_LIMBS[precomputation.field]
+    a = _u64(coefficients).reshape(-1, L)
+    out = np.empty((precomputation.size(), L), dtype=np.uint64)
+    _check(lib().plk_divide_by_z_h(precomputation.handle, _p64(a), a.shape[0], n_gates, _p64(out)))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers on the same arithmetic
+# ------------------------------------------------------------------------------------------------
+_OPS = dict(add=0, sub=1, mul=2, square=3, neg=4, inverse=5, to_canonical=6, from_canonical=7, double=8)
+
+
+def field_op(field: int, op: str, a, b=None) -> np.ndarray:
+    L = FIELD_LIMBS[field]
+    a = _u64(a).reshape(-1, L)
+    out = np.empty_like(a)
+    bp = _p64(_u64(b).reshape(-1, L)) if b is not None else None
+    _check(lib().plk_field_op(field, _OPS[op], _p64(a), bp, _p64(out), a.shape[0]))
+    return out
+
+
+def batch_multiplicative_inverse(field: int, x) -> np.ndarray:
+    """Field::batch_multiplicative_inverse (src/field/field.rs:251-278); panics on a zero input."""
+    L = FIELD_LIMBS[field]
+    a = _u64(x).reshape(-1, L)
+    out = np.empty_like(a)
+    _check(lib().plk_batch_inverse(field, _p64(a), _p64(out), a.shape[0]))
+    return out
+
+
+def batch_to_affine(curve: int, points_xyz, zero=None):
+    """ProjectivePoint::batch_to_affine (src/curve/curve.rs:216-232)."""
+    Lb = FIELD_LIMBS[CURVE_BASE_FIELD[curve]]
+    g = _u64(points_xyz).reshape(-1, 3, Lb)
+    n = g.shape[0]
+    z = _zero_flags(zero, n)
+    out = np.zeros((n, 2, Lb), dtype=np.uint64)
+    oz = np.zeros(n, dtype=np.uint8)
+    _check(lib().plk_batch_to_affine(curve, _p64(g), _p8(z), n, _p64(out), _p8(oz)))
+    return out, oz
+
+
+def points_generate(curve: int, seed: int, n: int) -> np.ndarray:
+    """Synthetic generators P_i = [splitmix64(seed + i)] G as (n, 2, L) affine Montgomery limbs."""
+    Lb = FIELD_LIMBS[CURVE_BASE_FIELD[curve]]
+    out = np.zeros((n, 2, Lb), dtype=np.uint64)
+    _check(lib().plk_points_generate(curve, seed, n, _p64(out)))
+    return out

@@ -40,7 +40,7 @@ struct XYZZ {
     XYZZ r; r.x = p.x; r.y = p.y; r.zz = F::one(); r.zzz = F::one(); return r;
   }
   // 2*(x1, y1) for a non-identity affine point with y1 != 0 (always true in an odd-order group)
-  PLK_HD static XYZZ dbl_affine(const Affine<C>& p) {
+  PLK_HD_NOINLINE static XYZZ dbl_affine(const Affine<C>& p) {
     if (p.is_identity() || p.y.is_zero()) return identity();
     F u = F::dbl(p.y);
     F v = F::sqr(u);
@@ -55,7 +55,7 @@ struct XYZZ {
     r.zzz = w;
     return r;
   }
-  PLK_HD static XYZZ dbl(const XYZZ& p) {
+  PLK_HD_NOINLINE static XYZZ dbl(const XYZZ& p) {
     if (p.is_identity() || p.y.is_zero()) return identity();
     F u = F::dbl(p.y);
     F v = F::sqr(u);
@@ -93,7 +93,7 @@ struct XYZZ {
     return o;
   }
   // a + b (value of curve_adds.rs:5-48)
-  PLK_HD static XYZZ add(const XYZZ& a, const XYZZ& b) {
+  PLK_HD_NOINLINE static XYZZ add(const XYZZ& a, const XYZZ& b) {
     if (a.is_identity()) return b;
     if (b.is_identity()) return a;
     F u1 = F::mul(a.x, b.zz);
@@ -118,7 +118,7 @@ struct XYZZ {
   }
   PLK_HD static XYZZ neg(const XYZZ& a) { XYZZ r = a; r.y = F::neg(a.y); return r; }
   // to_affine (curve.rs:206-214): one inversion of ZZ*ZZZ
-  PLK_HD static Affine<C> to_affine(const XYZZ& a) {
+  PLK_HD_NOINLINE static Affine<C> to_affine(const XYZZ& a) {
     if (a.is_identity()) return Affine<C>::identity();
     F j = F::inverse(F::mul(a.zz, a.zzz));
     Affine<C> r;
@@ -127,7 +127,7 @@ struct XYZZ {
     return r;
   }
   // [k] p for a small scalar k (double-and-add, MSB first)
-  PLK_HD static XYZZ mul_u64(const XYZZ& p, uint64_t k) {
+  PLK_HD_NOINLINE static XYZZ mul_u64(const XYZZ& p, uint64_t k) {
     XYZZ acc = identity();
     for (int i = 63; i >= 0; --i) {
       acc = dbl(acc);

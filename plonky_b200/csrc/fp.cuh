@@ -21,10 +21,14 @@
 #define __host__
 #define __device__
 #define __forceinline__ inline
+#define __noinline__ __attribute__((noinline))
 #endif
 #include "field_constants.cuh"
 
 #define PLK_HD __host__ __device__ __forceinline__
+// Cold paths (inversion, full group additions in the reduction tails) are real function calls: inlining
+// dozens of 150-instruction Montgomery products per call site buys nothing there and costs minutes of ptxas.
+#define PLK_HD_NOINLINE __host__ __device__ __noinline__
 
 namespace plk {
 // -p^-1 mod 2^32 is 0xffffffff for all four moduli (each is 1 mod 2^32).  It is deliberately read
@@ -252,7 +256,7 @@ struct Fp {
   PLK_HD static Fp from_canonical(const Fp& c) { return mul(c, r2()); }
 
   // a^e for a little-endian exponent of nbits bits (field.rs:309-330, same value)
-  PLK_HD static Fp pow(const Fp& a, const uint32_t* e, int nbits) {
+  PLK_HD_NOINLINE static Fp pow(const Fp& a, const uint32_t* e, int nbits) {
     Fp cur = a, prod = one();
     for (int i = 0; i < nbits; ++i) {
       if ((e[i >> 5] >> (i & 31)) & 1) prod = mul(prod, cur);
@@ -262,7 +266,7 @@ struct Fp {
   }
   // a^-1 by Fermat (the reference uses a binary GCD, bigint_inverse.rs:6-55 + monty.rs:162-167; the
   // inverse is unique, so the representative is identical).  a must be non-zero.
-  PLK_HD static Fp inverse(const Fp& a) {
+  PLK_HD_NOINLINE static Fp inverse(const Fp& a) {
     uint32_t e[N];
     // e = p - 2  (p is odd and p0 >= 3 for every modulus here? p0 = 1 -> borrow) -- do it generally
     uint32_t borrow = 0;

@@ -1,360 +1,25 @@
-// Multi-scalar multiplication for sm_100a: sum_i s_i * P_i over Tweedledee / Tweedledum / BLS12-377 G1.
-//
-// Replaces src/curve/curve_msm.rs of the reference: msm_precompute (:27-52), msm_execute (:63-100),
-// msm_execute_parallel (:102-157), msm_parallel (:54-61), to_digits (:159-180), and through them
-// pedersen_hash (src/plonk_util.rs:193-198).  The reference is a Yao-style method: per-generator
-// precomputed powers [(2^w)^j] G_i and ONE shared set of 2^w buckets, per-bucket batched-affine
-// sums on rayon workers, then a sequential running sum.  The result is the unique group element
-// sum_i s_i P_i, so any window size / coordinate system gives the same normalised point (F3, F5
-// in SURVEY.md); the caller's `w` is kept only for interface fidelity.
-//
-// Device pipeline (per execute, all on one stream, no host round trip):
-//   1. msm_count_kernel     scalars Montgomery -> canonical (one product by 1, = to_canonical_u64_vec),
-//                           signed c-bit window recoding (digits in [-2^(c-1), 2^(c-1)]),
-//                           histogram of |digit| over 2^(c-1) shared buckets (all windows share the
-//                           buckets because the table holds [2^(c j)] P_i -- the reference's own trick)
-//   2. msm_scan_kernel      exclusive scans: bucket offsets and task offsets (ceil(count / S) tasks)
-//   3. msm_scatter_kernel   counting-sort scatter of (window, point) ids + sign into bucket order
-//   4. msm_accumulate_kernel one thread per task: <= S mixed additions XYZZ += affine, points gathered
-//                           from the table with 128-bit loads, next point prefetched
-//   5. msm_bucket_sum_kernel one thread per bucket: sum of its task partials
-//   6. msm_range_kernel     running sums over ranges of buckets + [lo] * range sum
-//   7. msm_final_kernel     tree reduction of the range partials, to_affine
-// Exceptional cases (identity, P == Q, P == -Q) are handled in every addition like the reference
-// (src/curve/curve_adds.rs:12-33, src/curve/curve_summations.rs:107-141).
-//
-// Roofline accounting: algorithmic bytes = n * (32 + 2 * 8L); the table walk reads
-// nwin * 2 * 8L bytes per term instead of one point (the reference streams its table the same way).
-#include <mutex>
-#include "common.cuh"
-#include "ec.cuh"
-
-namespace plk {
-
-constexpr int kTaskSize = 64;        // S: additions per accumulate task
-constexpr int kRangeSize = 8;        // buckets per running-sum range
-constexpr int kAccThreads = 128;
-
-struct MsmGeom {
-  unsigned long long n;     // terms
-  int c;                    // window bits
-  int nwin;                 // windows = ceil((BITS + 1) / c)
-  unsigned nb;              // buckets = 2^(c-1)
-};
-
-// signed window recoding of a canonical scalar; calls f(window, bucket_index, negative)
-template <class SF, class Fn>
-__device__ __forceinline__ void for_each_digit(const SF& canon, const MsmGeom& g, Fn&& f) {
-  unsigned carry = 0;
-  const unsigned full = 1u << g.c, halfw = 1u << (g.c - 1), mask = full - 1;
-  for (int j = 0; j < g.nwin; ++j) {
-    const int bit = j * g.c;
-    const int limb = bit >> 5, off = bit & 31;
-    unsigned long long two = 0;
-    if (limb < SF::N) two = canon.l[limb];
-    if (limb + 1 < SF::N) two |= (unsigned long long)canon.l[limb + 1] << 32;
-    unsigned raw = ((unsigned)(two >> off) & mask) + carry;
-    carry = 0;
-    if (raw > halfw) {
-      // digit = raw - 2^c (negative or, when raw == 2^c, zero), carry one into the next window
-      carry = 1;
-      if (raw != full) f(j, full - raw - 1, true);
-    } else if (raw != 0) {
-      f(j, raw - 1, false);
-    }
-  }
-}
-
-template <class C>
-__global__ void msm_count_kernel(const uint4* __restrict__ scalars, MsmGeom g, unsigned* __restrict__ counts) {
-  typedef Fp<typename C::Scalar> SF;
-  unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-  if (i >= g.n) return;
-  SF s = SF::to_canonical(load_fp<SF>(scalars, i));     // curve_msm.rs:164 to_canonical_u64_vec
-  for_each_digit(s, g, [&](int, unsigned b, bool) { atomicAdd(&counts[b], 1u); });
-}
-
-// single CTA: offsets[b] = exclusive sum of counts, task_off[b] = exclusive sum of ceil(count / S);
-// offsets[nb] / task_off[nb] = totals; cursors[b] = offsets[b] (scatter positions)
-__global__ void msm_scan_kernel(const unsigned* __restrict__ counts, unsigned nb, unsigned* __restrict__ offsets,
-                                unsigned* __restrict__ task_off, unsigned* __restrict__ cursors) {
-  __shared__ unsigned s_a[1024], s_b[1024];
-  __shared__ unsigned carry_a, carry_b;
-  if (threadIdx.x == 0) { carry_a = 0; carry_b = 0; }
-  __syncthreads();
-  for (unsigned base = 0; base < nb; base += 1024) {
-    unsigned i = base + threadIdx.x;
-    unsigned ca = i < nb ? counts[i] : 0;
-    unsigned cb = (ca + kTaskSize - 1) / kTaskSize;
-    s_a[threadIdx.x] = ca;
-    s_b[threadIdx.x] = cb;
-    __syncthreads();
-    for (unsigned d = 1; d < 1024; d <<= 1) {
-      unsigned va = 0, vb = 0;
-      if (threadIdx.x >= d) { va = s_a[threadIdx.x - d]; vb = s_b[threadIdx.x - d]; }
-      __syncthreads();
-      s_a[threadIdx.x] += va;
-      s_b[threadIdx.x] += vb;
-      __syncthreads();
-    }
-    if (i < nb) {
-      unsigned ea = carry_a + s_a[threadIdx.x] - ca;
-      offsets[i] = ea;
-      cursors[i] = ea;
-      task_off[i] = carry_b + s_b[threadIdx.x] - cb;
-    }
-    __syncthreads();
-    if (threadIdx.x == 1023) { carry_a += s_a[1023]; carry_b += s_b[1023]; }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) { offsets[nb] = carry_a; task_off[nb] = carry_b; }
-}
-
-template <class C>
-__global__ void msm_scatter_kernel(const uint4* __restrict__ scalars, MsmGeom g, unsigned* __restrict__ cursors,
-                                   unsigned* __restrict__ sorted) {
-  typedef Fp<typename C::Scalar> SF;
-  unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-  if (i >= g.n) return;
-  SF s = SF::to_canonical(load_fp<SF>(scalars, i));
-  for_each_digit(s, g, [&](int j, unsigned b, bool negative) {
-    unsigned pos = atomicAdd(&cursors[b], 1u);
-    // entry = table slot (window-major: j * n + i) with the sign in bit 31 (n * nwin < 2^31 checked on host)
-    sorted[pos] = (unsigned)((unsigned long long)j * g.n + i) | (negative ? 0x80000000u : 0u);
-  });
-}
-
-template <class C>
-__device__ __forceinline__ Affine<C> load_affine(const void* table, size_t slot) {
-  typedef Fp<typename C::Base> F;
-  Affine<C> a;
-  a.x = load_fp<F>(table, 2 * slot);
-  a.y = load_fp<F>(table, 2 * slot + 1);
-  return a;
-}
-template <class C>
-__device__ __forceinline__ void store_xyzz(void* base, size_t idx, const XYZZ<C>& p) {
-  typedef Fp<typename C::Base> F;
-  store_fp<F>(base, 4 * idx, p.x);
-  store_fp<F>(base, 4 * idx + 1, p.y);
-  store_fp<F>(base, 4 * idx + 2, p.zz);
-  store_fp<F>(base, 4 * idx + 3, p.zzz);
-}
-template <class C>
-__device__ __forceinline__ XYZZ<C> load_xyzz(const void* base, size_t idx) {
-  typedef Fp<typename C::Base> F;
-  XYZZ<C> p;
-  p.x = load_fp<F>(base, 4 * idx);
-  p.y = load_fp<F>(base, 4 * idx + 1);
-  p.zz = load_fp<F>(base, 4 * idx + 2);
-  p.zzz = load_fp<F>(base, 4 * idx + 3);
-  return p;
-}
-
-// one thread per task: task t of bucket b adds entries [offsets[b] + k S, min(offsets[b+1], .. + S))
-template <class C>
-__global__ void __launch_bounds__(kAccThreads) msm_accumulate_kernel(const void* __restrict__ table, const unsigned* __restrict__ sorted,
-                                                                     const unsigned* __restrict__ offsets,
-                                                                     const unsigned* __restrict__ task_off, unsigned nb,
-                                                                     void* __restrict__ partials) {
-  typedef Fp<typename C::Base> F;
-  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned total = task_off[nb];
-  if (t >= total) return;
-  // bucket of task t: last b with task_off[b] <= t
-  unsigned lo = 0, hi = nb;
-  while (hi - lo > 1) {
-    unsigned mid = (lo + hi) >> 1;
-    if (task_off[mid] <= t) lo = mid; else hi = mid;
-  }
-  const unsigned b = lo;
-  const unsigned start = offsets[b] + (t - task_off[b]) * kTaskSize;
-  unsigned end = offsets[b + 1];
-  if (end > start + kTaskSize) end = start + kTaskSize;
-  XYZZ<C> acc = XYZZ<C>::identity();
-  unsigned e = sorted[start];
-  Affine<C> next = load_affine<C>(table, e & 0x7fffffffu);
-  for (unsigned k = start; k < end; ++k) {
-    Affine<C> p = next;
-    const bool negative = (e >> 31) != 0;
-    if (k + 1 < end) {
-      e = sorted[k + 1];
-      next = load_affine<C>(table, e & 0x7fffffffu);
-    }
-    if (negative) p.y = F::neg(p.y);
-    acc = XYZZ<C>::madd(acc, p);
-  }
-  store_xyzz<C>(partials, t, acc);
-}
-
-template <class C>
-__global__ void msm_bucket_sum_kernel(const void* __restrict__ partials, const unsigned* __restrict__ task_off, unsigned nb,
-                                      void* __restrict__ buckets) {
-  const unsigned b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nb) return;
-  XYZZ<C> acc = XYZZ<C>::identity();
-  for (unsigned t = task_off[b]; t < task_off[b + 1]; ++t) acc = XYZZ<C>::add(acc, load_xyzz<C>(partials, t));
-  store_xyzz<C>(buckets, b, acc);
-}
-
-// bucket index b carries weight (b + 1).  Range [lo, lo + R): sum_b (b + 1) B_b =
-//   sum_b (b - lo + 1) B_b  (running sum, curve_msm.rs:149-154)  +  lo * sum_b B_b
-template <class C>
-__global__ void msm_range_kernel(const void* __restrict__ buckets, unsigned nb, void* __restrict__ range_out) {
-  const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned lo = r * kRangeSize;
-  if (lo >= nb) return;
-  unsigned hi = lo + kRangeSize;
-  if (hi > nb) hi = nb;
-  XYZZ<C> run = XYZZ<C>::identity(), sum = XYZZ<C>::identity();
-  for (unsigned b = hi; b-- > lo;) {
-    run = XYZZ<C>::add(run, load_xyzz<C>(buckets, b));
-    sum = XYZZ<C>::add(sum, run);
-  }
-  if (lo != 0 && !run.is_identity()) sum = XYZZ<C>::add(sum, XYZZ<C>::mul_u64(run, lo));
-  store_xyzz<C>(range_out, r, sum);
-}
-
-// single CTA: sum `count` XYZZ points; optionally normalise to (x, y, z = 1 | zero flag)
-template <class C>
-__global__ void msm_final_kernel(const void* __restrict__ in, unsigned count, void* __restrict__ out_xyzz,
-                                 uint32_t* __restrict__ out_xyz, unsigned char* __restrict__ out_zero) {
-  typedef Fp<typename C::Base> F;
-  extern __shared__ uint4 sm[];
-  XYZZ<C> acc = XYZZ<C>::identity();
-  for (unsigned i = threadIdx.x; i < count; i += blockDim.x) acc = XYZZ<C>::add(acc, load_xyzz<C>(in, i));
-  store_xyzz<C>(sm, threadIdx.x, acc);
-  __syncthreads();
-  for (unsigned d = blockDim.x >> 1; d > 0; d >>= 1) {
-    if (threadIdx.x < d) {
-      XYZZ<C> a = load_xyzz<C>(sm, threadIdx.x), b = load_xyzz<C>(sm, threadIdx.x + d);
-      store_xyzz<C>(sm, threadIdx.x, XYZZ<C>::add(a, b));
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    XYZZ<C> total = load_xyzz<C>(sm, 0);
-    if (out_xyzz) store_xyzz<C>(out_xyzz, 0, total);
-    if (out_xyz) {
-      Affine<C> a = XYZZ<C>::to_affine(total);
-      const bool z = total.is_identity();
-      F one = z ? F::zero() : F::one();
-      for (int i = 0; i < F::N; ++i) {
-        out_xyz[i] = a.x.l[i];
-        out_xyz[F::N + i] = a.y.l[i];
-        out_xyz[2 * F::N + i] = one.l[i];
-      }
-      *out_zero = z ? 1 : 0;
-    }
-  }
-}
-
-// ---- table construction: [2^(c j)] P_i for j < nwin (curve_msm.rs:40-52 with our own window) ----
-template <class C>
-__global__ void __launch_bounds__(128) msm_table_kernel(const void* __restrict__ points, unsigned long long n, int c, int nwin,
-                                                        void* __restrict__ table) {
-  typedef Fp<typename C::Base> F;
-  const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  Affine<C> p = load_affine<C>(points, i);
-  // window 0 is the point itself
-  store_fp<F>(table, 2 * i, p.x);
-  store_fp<F>(table, 2 * i + 1, p.y);
-  XYZZ<C> q = XYZZ<C>::from_affine(p);
-  for (int j = 1; j < nwin; ++j) {
-    for (int k = 0; k < c; ++k) q = XYZZ<C>::dbl(q);
-    // normalise this power and restart from the affine form: keeps the inversion count at one per
-    // power but needs no second pass or extra memory (table construction is amortised over all
-    // executes against the same generators, like msm_precompute in the reference).
-    Affine<C> a = XYZZ<C>::to_affine(q);
-    store_fp<F>(table, 2 * ((size_t)j * n + i), a.x);
-    store_fp<F>(table, 2 * ((size_t)j * n + i) + 1, a.y);
-    q = XYZZ<C>::from_affine(a);
-  }
-}
-
-// projective (x, y, z, zero) / affine (x, y, zero) host layouts -> device affine with identity = (0, 0)
-template <class C>
-__global__ void msm_import_points_kernel(const void* __restrict__ in, const unsigned char* __restrict__ zero, unsigned long long n,
-                                         int projective, void* __restrict__ out) {
-  typedef Fp<typename C::Base> F;
-  const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  Affine<C> a;
-  bool z = zero && zero[i];
-  if (projective) {
-    F x = load_fp<F>(in, 3 * i), y = load_fp<F>(in, 3 * i + 1), zz = load_fp<F>(in, 3 * i + 2);
-    if (z || zz.is_zero()) a = Affine<C>::identity();
-    else if (zz == F::one()) { a.x = x; a.y = y; }
-    else { F zi = F::inverse(zz); a.x = F::mul(x, zi); a.y = F::mul(y, zi); }   // curve.rs:206-214
-  } else {
-    a.x = load_fp<F>(in, 2 * i);
-    a.y = load_fp<F>(in, 2 * i + 1);
-    if (z) a = Affine<C>::identity();
-  }
-  store_fp<F>(out, 2 * i, a.x);
-  store_fp<F>(out, 2 * i + 1, a.y);
-}
-
-// P_i = [splitmix64(seed + i)] G (synthetic generators; same recipe as oracle/ref_port.cpp gen_points_t)
-__device__ __forceinline__ unsigned long long splitmix_hash(unsigned long long z) {
-  z += 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  return z ^ (z >> 31);
-}
-template <class C>
-__global__ void __launch_bounds__(128) points_generate_kernel(Affine<C> gen, unsigned long long seed, unsigned long long n, void* __restrict__ out) {
-  typedef Fp<typename C::Base> F;
-  const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const unsigned long long k = splitmix_hash(seed + i);
-  XYZZ<C> acc = XYZZ<C>::identity();
-  const XYZZ<C> g = XYZZ<C>::from_affine(gen);
-  for (int b = 63; b >= 0; --b) {
-    acc = XYZZ<C>::dbl(acc);
-    if ((k >> b) & 1) acc = XYZZ<C>::madd(acc, gen);
-  }
-  (void)g;
-  Affine<C> a = XYZZ<C>::to_affine(acc);
-  store_fp<F>(out, 2 * i, a.x);
-  store_fp<F>(out, 2 * i + 1, a.y);
-}
-
-// normalise n projective points (batch_to_affine, curve.rs:216-232): one thread per point
-template <class C>
-__global__ void batch_to_affine_kernel(const void* __restrict__ in, const unsigned char* __restrict__ zero, unsigned long long n,
-                                       void* __restrict__ out_xy, unsigned char* __restrict__ out_zero) {
-  typedef Fp<typename C::Base> F;
-  const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  F x = load_fp<F>(in, 3 * i), y = load_fp<F>(in, 3 * i + 1), z = load_fp<F>(in, 3 * i + 2);
-  const bool isz = (zero && zero[i]);
-  if (isz) { x = F::zero(); y = F::zero(); }
-  else { F zi = F::inverse(z); x = F::mul(x, zi); y = F::mul(y, zi); }
-  store_fp<F>(out_xy, 2 * i, x);
-  store_fp<F>(out_xy, 2 * i + 1, y);
-  out_zero[i] = isz ? 1 : 0;
-}
-
-}  // namespace plk
+// C ABI of the MSM (include/plonky_b200.h); kernels live in msm_kernels.cuh, one translation unit per curve.
+#include "msm_plan.h"
+#include "field_constants.cuh"
 
 using namespace plk;
 
-struct plk_msm_table {
-  int curve = 0;
-  size_t n = 0;
-  unsigned w = 0;          // the caller's window (interface fidelity only)
-  MsmGeom g;
-  size_t point_bytes = 64; // affine point
-  DevBuf table;            // nwin * n affine points, window-major
-  // scratch (one execute at a time per table)
-  std::mutex mu;
-  DevBuf counts, offsets, task_off, cursors, sorted, partials, buckets, ranges, result;
-  size_t max_tasks = 0;
-};
+namespace plk {
+const MsmOps* msm_ops_tweedledee();
+const MsmOps* msm_ops_tweedledum();
+const MsmOps* msm_ops_bls12_377();
+}
 
 namespace {
+
+const MsmOps* ops_for(int curve) {
+  switch (curve) {
+    case PLK_CURVE_TWEEDLEDEE: return msm_ops_tweedledee();
+    case PLK_CURVE_TWEEDLEDUM: return msm_ops_tweedledum();
+    case PLK_CURVE_BLS12_377: return msm_ops_bls12_377();
+  }
+  fail(PLK_EINVAL, "unknown curve id");
+}
 
 int curve_scalar_bits(int curve) {
   switch (curve) {
@@ -376,33 +41,6 @@ int pick_window(size_t n) {
   return c;
 }
 
-#define PLK_CURVE_DISPATCH(curve, FN, ...)                                 \
-  switch (curve) {                                                          \
-    case PLK_CURVE_TWEEDLEDEE: FN<TweedledeeParams>(__VA_ARGS__); break;    \
-    case PLK_CURVE_TWEEDLEDUM: FN<TweedledumParams>(__VA_ARGS__); break;    \
-    case PLK_CURVE_BLS12_377: FN<Bls12377Params>(__VA_ARGS__); break;       \
-    default: fail(PLK_EINVAL, "unknown curve id");                          \
-  }
-
-template <class C>
-void table_build(plk_msm_table* t, const void* d_points, cudaStream_t st) {
-  typedef Fp<typename C::Base> F;
-  t->point_bytes = 2 * sizeof(F);
-  t->table.alloc((size_t)t->g.nwin * t->n * t->point_bytes);
-  if (t->n == 0) return;
-  unsigned blocks = (unsigned)((t->n + 127) / 128);
-  msm_table_kernel<C><<<blocks, 128, 0, st>>>(d_points, t->n, t->g.c, t->g.nwin, t->table.p);
-  PLK_LAUNCHED();
-}
-
-template <class C>
-void import_points(const void* d_raw, const unsigned char* d_zero, size_t n, int projective, void* d_out, cudaStream_t st) {
-  if (n == 0) return;
-  unsigned blocks = (unsigned)((n + 127) / 128);
-  msm_import_points_kernel<C><<<blocks, 128, 0, st>>>(d_raw, d_zero, n, projective, d_out);
-  PLK_LAUNCHED();
-}
-
 void alloc_scratch(plk_msm_table* t) {
   const MsmGeom& g = t->g;
   const size_t entries = (size_t)g.n * g.nwin;
@@ -417,73 +55,6 @@ void alloc_scratch(plk_msm_table* t) {
   t->buckets.alloc((size_t)g.nb * xyzz);
   t->ranges.alloc(((size_t)g.nb / kRangeSize + 1) * xyzz);
   t->result.alloc(xyzz + 3 * t->point_bytes / 2 + 16);
-}
-
-// the whole pipeline for one scalar vector; writes either the normalised point or the XYZZ partial
-template <class C>
-void execute_one(plk_msm_table* t, const void* d_scalars, void* d_out_xyz, void* d_out_zero, void* d_partial, cudaStream_t st) {
-  typedef Fp<typename C::Base> F;
-  const MsmGeom g = t->g;
-  const size_t xyzz = 4 * sizeof(F);
-  if (g.n == 0) {
-    // empty sum = identity (curve_msm.rs: y stays ProjectivePoint::ZERO)
-    if (d_partial) PLK_CUDA(cudaMemsetAsync(d_partial, 0, xyzz, st));
-    if (d_out_xyz) {
-      PLK_CUDA(cudaMemsetAsync(d_out_xyz, 0, 3 * sizeof(F), st));
-      PLK_CUDA(cudaMemsetAsync(d_out_zero, 1, 1, st));
-    }
-    return;
-  }
-  PLK_CUDA(cudaMemsetAsync(t->counts.p, 0, (size_t)g.nb * 4, st));
-  const unsigned sblocks = (unsigned)((g.n + 255) / 256);
-  msm_count_kernel<C><<<sblocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(d_scalars), g, t->counts.as<unsigned>());
-  PLK_LAUNCHED();
-  msm_scan_kernel<<<1, 1024, 0, st>>>(t->counts.as<unsigned>(), g.nb, t->offsets.as<unsigned>(), t->task_off.as<unsigned>(),
-                                      t->cursors.as<unsigned>());
-  PLK_LAUNCHED();
-  msm_scatter_kernel<C><<<sblocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(d_scalars), g, t->cursors.as<unsigned>(),
-                                                 t->sorted.as<unsigned>());
-  PLK_LAUNCHED();
-  const unsigned ablocks = (unsigned)((t->max_tasks + kAccThreads - 1) / kAccThreads);
-  msm_accumulate_kernel<C><<<ablocks, kAccThreads, 0, st>>>(t->table.p, t->sorted.as<unsigned>(), t->offsets.as<unsigned>(),
-                                                            t->task_off.as<unsigned>(), g.nb, t->partials.p);
-  PLK_LAUNCHED();
-  msm_bucket_sum_kernel<C><<<(g.nb + 127) / 128, 128, 0, st>>>(t->partials.p, t->task_off.as<unsigned>(), g.nb, t->buckets.p);
-  PLK_LAUNCHED();
-  const unsigned nranges = (g.nb + kRangeSize - 1) / kRangeSize;
-  msm_range_kernel<C><<<(nranges + 63) / 64, 64, 0, st>>>(t->buckets.p, g.nb, t->ranges.p);
-  PLK_LAUNCHED();
-  const unsigned fthreads = nranges >= 256 ? 256 : (nranges >= 32 ? 32 : 1);
-  msm_final_kernel<C><<<1, fthreads, fthreads * xyzz, st>>>(t->ranges.p, nranges, d_partial, reinterpret_cast<uint32_t*>(d_out_xyz),
-                                                            reinterpret_cast<unsigned char*>(d_out_zero));
-  PLK_LAUNCHED();
-}
-
-template <class C>
-void combine_partials(const void* d_partials, size_t count, void* d_out_xyz, void* d_out_zero, cudaStream_t st) {
-  typedef Fp<typename C::Base> F;
-  const unsigned fthreads = count >= 32 ? 32 : 1;
-  msm_final_kernel<C><<<1, fthreads, fthreads * 4 * sizeof(F), st>>>(d_partials, (unsigned)count, nullptr,
-                                                                     reinterpret_cast<uint32_t*>(d_out_xyz),
-                                                                     reinterpret_cast<unsigned char*>(d_out_zero));
-  PLK_LAUNCHED();
-}
-
-template <class C>
-void generate_points(uint64_t seed, size_t n, void* d_out, cudaStream_t st) {
-  typedef Fp<typename C::Base> F;
-  if (n == 0) return;
-  Affine<C> g;
-  for (int i = 0; i < F::N; ++i) { g.x.l[i] = CurveTables<C>::gen_x()[i]; g.y.l[i] = CurveTables<C>::gen_y()[i]; }
-  points_generate_kernel<C><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(g, seed, n, d_out);
-  PLK_LAUNCHED();
-}
-
-template <class C>
-void to_affine_batch(const void* d_in, const unsigned char* d_zero, size_t n, void* d_out, unsigned char* d_out_zero, cudaStream_t st) {
-  if (n == 0) return;
-  batch_to_affine_kernel<C><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_in, d_zero, n, d_out, d_out_zero);
-  PLK_LAUNCHED();
 }
 
 plk_msm_table* new_table(int curve, size_t n, unsigned w) {
@@ -516,8 +87,8 @@ void precompute_host(int curve, const uint64_t* pts, const uint8_t* zero, size_t
     DevBuf d_raw(raw_bytes), d_zero(n), d_aff(n * t->point_bytes);
     if (n) PLK_CUDA(cudaMemcpyAsync(d_raw.p, pts, raw_bytes, cudaMemcpyHostToDevice, st));
     if (n && zero) PLK_CUDA(cudaMemcpyAsync(d_zero.p, zero, n, cudaMemcpyHostToDevice, st));
-    PLK_CURVE_DISPATCH(curve, import_points, d_raw.p, zero ? d_zero.as<unsigned char>() : nullptr, n, projective, d_aff.p, st);
-    PLK_CURVE_DISPATCH(curve, table_build, t, d_aff.p, st);
+    ops_for(curve)->import_points(d_raw.p, zero ? d_zero.as<unsigned char>() : nullptr, n, projective, d_aff.p, st);
+    ops_for(curve)->table_build(t, d_aff.p, st);
     alloc_scratch(t);
     PLK_CUDA(cudaStreamSynchronize(st));
   } catch (...) {
@@ -539,7 +110,7 @@ void execute_host(plk_msm_table* t, const uint64_t* scalars, size_t n, size_t k,
   char* d_o = reinterpret_cast<char*>(thread_scratch(1, k * (3 * L * 8 + 8)));
   if (n) PLK_CUDA(cudaMemcpyAsync(d_s, scalars, sbytes * k, cudaMemcpyHostToDevice, st));
   for (size_t j = 0; j < k; ++j) {
-    PLK_CURVE_DISPATCH(t->curve, execute_one, t, d_s + j * sbytes, d_o + j * 3 * L * 8, d_o + k * 3 * L * 8 + j, nullptr, st);
+    ops_for(t->curve)->execute_one(t, d_s + j * sbytes, d_o + j * 3 * L * 8, d_o + k * 3 * L * 8 + j, nullptr, st);
   }
   PLK_CUDA(cudaMemcpyAsync(out_xyz, d_o, k * 3 * L * 8, cudaMemcpyDeviceToHost, st));
   PLK_CUDA(cudaMemcpyAsync(out_zero, d_o + k * 3 * L * 8, k, cudaMemcpyDeviceToHost, st));
@@ -565,7 +136,7 @@ int plk_msm_precompute_affine_dev(int curve, const void* d_points_xy, size_t n, 
     try {
       cudaStream_t st = thread_stream();
       t->point_bytes = 2 * curve_base_limbs64(curve) * 8;
-      PLK_CURVE_DISPATCH(curve, table_build, t, d_points_xy, st);
+      ops_for(curve)->table_build(t, d_points_xy, st);
       alloc_scratch(t);
       PLK_CUDA(cudaStreamSynchronize(st));
     } catch (...) {
@@ -609,7 +180,7 @@ int plk_msm_execute_dev(const plk_msm_table* tc, const void* d_scalars, size_t n
     if (n != t->n) fail(PLK_ELENGTH, "precomputation / scalars length mismatch");
     if ((n && !d_scalars) || !d_out_xyz || !d_out_zero) fail(PLK_EINVAL, "NULL buffer");
     std::lock_guard<std::mutex> lk(t->mu);
-    PLK_CURVE_DISPATCH(t->curve, execute_one, t, d_scalars, d_out_xyz, d_out_zero, nullptr, reinterpret_cast<cudaStream_t>(stream));
+    ops_for(t->curve)->execute_one(t, d_scalars, d_out_xyz, d_out_zero, nullptr, reinterpret_cast<cudaStream_t>(stream));
   });
 }
 int plk_msm_execute_partial_dev(const plk_msm_table* tc, const void* d_scalars, size_t n, void* d_partial, void* stream) {
@@ -619,13 +190,13 @@ int plk_msm_execute_partial_dev(const plk_msm_table* tc, const void* d_scalars, 
     if (n != t->n) fail(PLK_ELENGTH, "precomputation / scalars length mismatch");
     if ((n && !d_scalars) || !d_partial) fail(PLK_EINVAL, "NULL buffer");
     std::lock_guard<std::mutex> lk(t->mu);
-    PLK_CURVE_DISPATCH(t->curve, execute_one, t, d_scalars, nullptr, nullptr, d_partial, reinterpret_cast<cudaStream_t>(stream));
+    ops_for(t->curve)->execute_one(t, d_scalars, nullptr, nullptr, d_partial, reinterpret_cast<cudaStream_t>(stream));
   });
 }
 int plk_msm_combine_partials_dev(int curve, const void* d_partials, size_t count, void* d_out_xyz, void* d_out_zero, void* stream) {
   return guarded([&] {
     if (!d_partials || !d_out_xyz || !d_out_zero || count == 0) fail(PLK_EINVAL, "bad arguments");
-    PLK_CURVE_DISPATCH(curve, combine_partials, d_partials, count, d_out_xyz, d_out_zero, reinterpret_cast<cudaStream_t>(stream));
+    ops_for(curve)->combine_partials(d_partials, count, d_out_xyz, d_out_zero, reinterpret_cast<cudaStream_t>(stream));
   });
 }
 size_t plk_msm_partial_limbs(int curve) { return 4 * (size_t)curve_base_limbs64(curve); }
@@ -633,7 +204,7 @@ size_t plk_msm_partial_limbs(int curve) { return 4 * (size_t)curve_base_limbs64(
 int plk_points_generate_dev(int curve, uint64_t seed, size_t n, void* d_points_xy, void* stream) {
   return guarded([&] {
     if (n && !d_points_xy) fail(PLK_EINVAL, "NULL buffer");
-    PLK_CURVE_DISPATCH(curve, generate_points, seed, n, d_points_xy, reinterpret_cast<cudaStream_t>(stream));
+    ops_for(curve)->generate_points(seed, n, d_points_xy, reinterpret_cast<cudaStream_t>(stream));
   });
 }
 int plk_points_generate(int curve, uint64_t seed, size_t n, uint64_t* points_xy) {
@@ -643,7 +214,7 @@ int plk_points_generate(int curve, uint64_t seed, size_t n, uint64_t* points_xy)
     cudaStream_t st = thread_stream();
     const size_t bytes = n * 2 * curve_base_limbs64(curve) * 8;
     DevBuf d(bytes);
-    PLK_CURVE_DISPATCH(curve, generate_points, seed, n, d.p, st);
+    ops_for(curve)->generate_points(seed, n, d.p, st);
     PLK_CUDA(cudaMemcpyAsync(points_xy, d.p, bytes, cudaMemcpyDeviceToHost, st));
     PLK_CUDA(cudaStreamSynchronize(st));
   });
@@ -658,7 +229,7 @@ int plk_batch_to_affine(int curve, const uint64_t* points_xyz, const uint8_t* ze
     DevBuf d_in(n * 3 * L * 8), d_z(n), d_out(n * 2 * L * 8), d_oz(n);
     PLK_CUDA(cudaMemcpyAsync(d_in.p, points_xyz, n * 3 * L * 8, cudaMemcpyHostToDevice, st));
     if (zero) PLK_CUDA(cudaMemcpyAsync(d_z.p, zero, n, cudaMemcpyHostToDevice, st));
-    PLK_CURVE_DISPATCH(curve, to_affine_batch, d_in.p, zero ? d_z.as<unsigned char>() : nullptr, n, d_out.p, d_oz.as<unsigned char>(), st);
+    ops_for(curve)->to_affine_batch(d_in.p, zero ? d_z.as<unsigned char>() : nullptr, n, d_out.p, d_oz.as<unsigned char>(), st);
     PLK_CUDA(cudaMemcpyAsync(out_xy, d_out.p, n * 2 * L * 8, cudaMemcpyDeviceToHost, st));
     PLK_CUDA(cudaMemcpyAsync(out_zero, d_oz.p, n, cudaMemcpyDeviceToHost, st));
     PLK_CUDA(cudaStreamSynchronize(st));

@@ -1,0 +1,3 @@
+// MSM kernels instantiated for one curve (separate translation unit: ptxas time runs in parallel).
+#include "msm_kernels.cuh"
+namespace plk { const MsmOps* msm_ops_tweedledee() { return make_msm_ops<TweedledeeParams>(); } }

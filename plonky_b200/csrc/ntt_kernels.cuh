@@ -1,0 +1,316 @@
+// Radix-2 NTT over the Tweedle / BLS12-377 prime fields for sm_100a.
+//
+// Replaces src/fft.rs of the reference: fft_precompute (:47-59), fft_with_precomputation (:61-80),
+// fft_with_precomputation_power_of_2 (:103-156), ifft_with_precomputation_power_of_2 (:82-101),
+// plus the coset / zero-pad callers in src/polynomial.rs:135-151,330-380 and
+// src/plonk_util.rs:169-190.  Same contract: natural order in, natural order out,
+// out[k] = sum_j c_j w^(jk) with w = primitive_root_of_unity(log2 n) (src/field/field.rs:429-435).
+//
+// Design (B200-first, nothing like the reference's log n passes over a 2n-entry table):
+//   n = R_1 * R_2 * ... * R_m, R_i = 2^r_i <= 256, m = ceil(log n / 8) passes (3 for 2^24).
+//   Input index  j = j_1 + R_1 j_2 + R_1 R_2 j_3 + ...      (j_1 least significant)
+//   Output index k = k_m + R_m k_{m-1} + ...                (k_1 most significant)
+//   Pass 1 transforms over j_m (input stride n/R_m) and writes the "work layout" in which the
+//   remaining digits are stored most-significant-first (a mixed-radix digit reversal), so that
+//   every later pass d = m-1 .. 1 is an IN-PLACE strided transform over j_d preceded by the twiddle
+//   w_{N_d}^(j_d k''), N_d = R_d M_d, M_d = R_{d+1}..R_m, k'' = the already transformed low part.
+//   After the last pass the data is in natural order: no separate bit-reversal pass ever runs.
+//   Each CTA owns a tile of 2^r rows x 8 columns (8 x 32 B = 256 B contiguous per row: full-sector
+//   128-bit loads), staged in shared memory as split 16-byte pieces with an XOR swizzle so that
+//   row-wise, column-wise and butterfly accesses are all bank-conflict free.  Butterflies run as
+//   radix-8 / 4 / 2 register rounds (3 / 2 / 1 layers per shared-memory round trip).
+//   Twiddles: sub-transform twiddles from a 128-entry table; inter-pass twiddles w_n^e on the fly
+//   from two small tables (w^lo, w^(hi << lo_bits)) and one multiply -- never an n-entry table.
+//   Fused: zero-padding (rows beyond n_in are never read), coset shift c_j g^j on load, n^-1 folded
+//   into the last pass' twiddle table for the inverse, g^-i / pointwise factors on the final store.
+//
+// Cost model for the roofline: algorithmic bytes = 2 * n * 32; this implementation moves
+// m * 2 * n * 32 bytes; arithmetic ~ (n/2) log n + 2 n (m-1) Montgomery products.
+#pragma once
+#include "ntt_plan.h"
+#include "fp.cuh"
+
+namespace plk {
+
+struct NttPassParams {
+  const void* in;
+  void* out;
+  int log_n;
+  int r;            // this pass' digit
+  int log_m;        // log2 M_d (in-place passes)
+  int log_t;        // log2 columns per tile
+  int first;        // 1: gathering pass, 0: in-place pass
+  int last;         // 1: this pass produces the final natural-order output
+  int ndig;         // number of low digits (m-1) for the digit reversal of the first pass
+  int digs[kMaxDigits];
+  unsigned long long n_in;        // first pass: elements actually present in the input row
+  unsigned long long in_stride;   // elements between batch rows
+  unsigned long long out_stride;
+  const void* wsub;               // w_256^k, k < 128
+  const void* tw_lo;              // w_n^e, e < 2^lo_bits
+  const void* tw_hi;              // w_n^(e << lo_bits)
+  int lo_bits;
+  int tw_all;                     // also multiply row 0 (n^-1 folded into tw_hi)
+  const void* pre_lo;             // optional input multiplier s^j (two-level, same lo_bits)
+  const void* pre_hi;
+  const void* post_lo;            // optional output multiplier s^k (two-level)
+  const void* post_hi;
+  const void* post_periodic;      // optional output multiplier tbl[k & post_mask]
+  unsigned long long post_mask;
+  const void* scale;              // optional constant multiplier (single-pass inverse)
+};
+
+__device__ __forceinline__ unsigned bitrev(unsigned x, int bits) { return bits == 0 ? 0u : (__brev(x) >> (32 - bits)); }
+
+template <class F>
+__device__ __forceinline__ F lds_fp(const uint4* smem, int elems, int sidx) {
+  F r;
+#pragma unroll
+  for (int pc = 0; pc < F::N / 4; ++pc) {
+    uint4 v = smem[pc * elems + sidx];
+    r.l[4 * pc] = v.x; r.l[4 * pc + 1] = v.y; r.l[4 * pc + 2] = v.z; r.l[4 * pc + 3] = v.w;
+  }
+  return r;
+}
+template <class F>
+__device__ __forceinline__ void sts_fp(uint4* smem, int elems, int sidx, const F& a) {
+#pragma unroll
+  for (int pc = 0; pc < F::N / 4; ++pc)
+    smem[pc * elems + sidx] = make_uint4(a.l[4 * pc], a.l[4 * pc + 1], a.l[4 * pc + 2], a.l[4 * pc + 3]);
+}
+template <class F>
+__device__ __forceinline__ F two_level(const void* lo, const void* hi, int lo_bits, unsigned long long e) {
+  F a = load_fp<F>(lo, (size_t)(e & ((1ull << lo_bits) - 1)));
+  unsigned long long h = e >> lo_bits;
+  if (h == 0) return a;                      // hi[0] == 1 for every non-folded table
+  return F::mul(a, load_fp<F>(hi, (size_t)h));
+}
+template <class F>
+__device__ __forceinline__ F two_level_always(const void* lo, const void* hi, int lo_bits, unsigned long long e) {
+  F a = load_fp<F>(lo, (size_t)(e & ((1ull << lo_bits) - 1)));
+  return F::mul(a, load_fp<F>(hi, (size_t)(e >> lo_bits)));
+}
+
+// Q layers of decimation-in-time butterflies on 2^Q register-resident elements whose rows are
+// base + (e << l0); `low` = base mod 2^l0 selects the twiddles.  LAYER0: l0 == 0 (twiddle 1 skipped).
+template <class F, int Q, bool LAYER0>
+__device__ __forceinline__ void dit_layers(F (&x)[1 << Q], int l0, int low, const void* wsub) {
+#pragma unroll
+  for (int t = 1; t <= Q; ++t) {
+    const int half = 1 << (t - 1);
+#pragma unroll
+    for (int kk = 0; kk < half; ++kk) {
+      const bool trivial = LAYER0 && kk == 0;
+      F w;
+      if (!trivial) w = load_fp<F>(wsub, (size_t)((low + (kk << l0)) << (kSubLog - (l0 + t))));
+#pragma unroll
+      for (int blk = 0; blk < (1 << Q); blk += 2 * half) {
+        F v = trivial ? x[blk + kk + half] : F::mul(x[blk + kk + half], w);
+        F u = x[blk + kk];
+        x[blk + kk] = F::add(u, v);
+        x[blk + kk + half] = F::sub(u, v);
+      }
+    }
+  }
+}
+
+// tile geometry shared by all phases of one CTA
+struct TileGeom {
+  unsigned long long gbase;   // global element index of (row 0, col 0)
+  int rowshift;               // global row stride = 1 << rowshift
+  unsigned long long k0;      // in-place: k'' of column 0 ; first: jlow of column 0
+};
+
+template <class F, int Q, bool LAYER0>
+__device__ __forceinline__ void ntt_round(const NttPassParams& p, uint4* smem, int l0) {
+  const int T = 1 << p.log_t, elems = 1 << (p.r + p.log_t);
+  const int groups = elems >> Q;
+  for (int gi = threadIdx.x; gi < groups; gi += blockDim.x) {
+    const int col = gi & (T - 1);
+    const int gr = gi >> p.log_t;
+    const int low = gr & ((1 << l0) - 1);
+    const int base_row = low | ((gr >> l0) << (l0 + Q));
+    F x[1 << Q];
+#pragma unroll
+    for (int e = 0; e < (1 << Q); ++e) {
+      const int row = base_row + (e << l0);
+      x[e] = lds_fp<F>(smem, elems, row * T + (col ^ (row & (T - 1))));
+    }
+    dit_layers<F, Q, LAYER0>(x, l0, low, p.wsub);
+#pragma unroll
+    for (int e = 0; e < (1 << Q); ++e) {
+      const int row = base_row + (e << l0);
+      sts_fp<F>(smem, elems, row * T + (col ^ (row & (T - 1))), x[e]);
+    }
+  }
+  __syncthreads();
+}
+
+
+// Input-side factors, applied once per element in shared memory before the butterflies (rows sit at
+// their bit-reversed position): coset shift s^j (first pass), inter-pass twiddle w_{N_d}^(j_d k'')
+// (in-place passes; n^-1 folded into the table on the last inverse pass), constant scale.
+template <class F>
+__device__ __noinline__ void ntt_pre_factors(const NttPassParams& p, const TileGeom& g, uint4* smem) {
+  const int T = 1 << p.log_t, elems = 1 << (p.r + p.log_t);
+  for (int idx = threadIdx.x; idx < elems; idx += blockDim.x) {
+    const int col = idx & (T - 1);
+    const int srow = idx >> p.log_t;
+    const unsigned orow = bitrev((unsigned)srow, p.r);
+    const int sidx = srow * T + (col ^ (srow & (T - 1)));
+    F fac;
+    bool have = false;
+    if (p.first) {
+      const unsigned long long j = g.gbase + col + ((unsigned long long)orow << g.rowshift);
+      if (p.pre_lo && j < p.n_in && j != 0) { fac = two_level<F>(p.pre_lo, p.pre_hi, p.lo_bits, j); have = true; }
+    } else {
+      const unsigned long long kk = g.k0 + col;
+      const unsigned long long ex = ((unsigned long long)orow * kk) << (p.log_n - p.r - p.log_m);
+      if (p.tw_all) { fac = two_level_always<F>(p.tw_lo, p.tw_hi, p.lo_bits, ex); have = true; }
+      else if (ex != 0) { fac = two_level<F>(p.tw_lo, p.tw_hi, p.lo_bits, ex); have = true; }
+    }
+    if (p.scale) {
+      F s = load_fp<F>(p.scale, 0);
+      fac = have ? F::mul(fac, s) : s;
+      have = true;
+    }
+    if (have) sts_fp<F>(smem, elems, sidx, F::mul(lds_fp<F>(smem, elems, sidx), fac));
+  }
+  __syncthreads();
+}
+// Output-side factors on the final natural-order values: s^-k (inverse coset) and / or a periodic table.
+template <class F>
+__device__ __noinline__ void ntt_post_factors(const NttPassParams& p, const TileGeom& g, uint4* smem) {
+  const int T = 1 << p.log_t, elems = 1 << (p.r + p.log_t);
+  for (int idx = threadIdx.x; idx < elems; idx += blockDim.x) {
+    const int col = idx & (T - 1);
+    const unsigned long long row = idx >> p.log_t;
+    const int sidx = (int)row * T + (col ^ ((int)row & (T - 1)));
+    const unsigned long long k = p.first ? row : (g.k0 + col + (row << p.log_m));
+    F x = lds_fp<F>(smem, elems, sidx);
+    if (p.post_lo && k != 0) x = F::mul(x, two_level<F>(p.post_lo, p.post_hi, p.lo_bits, k));
+    if (p.post_periodic) x = F::mul(x, load_fp<F>(p.post_periodic, (size_t)(k & p.post_mask)));
+    sts_fp<F>(smem, elems, sidx, x);
+  }
+  __syncthreads();
+}
+
+template <class F>
+__global__ void __launch_bounds__(kNttThreads, 2) ntt_pass_kernel(NttPassParams p) {
+  extern __shared__ uint4 smem[];
+  constexpr int PIECES = F::N / 4;
+  const int T = 1 << p.log_t, R = 1 << p.r, elems = R * T;
+  const unsigned long long tile = blockIdx.x;
+  const uint4* in = reinterpret_cast<const uint4*>(p.in) + (size_t)blockIdx.y * p.in_stride * PIECES;
+  uint4* out = reinterpret_cast<uint4*>(p.out) + (size_t)blockIdx.y * p.out_stride * PIECES;
+
+  TileGeom g;
+  if (p.first) {
+    g.k0 = tile << p.log_t;             // jlow of column 0
+    g.gbase = g.k0;
+    g.rowshift = p.log_n - p.r;         // input stride of j_m
+  } else {
+    const int tph = p.log_m - p.log_t;  // log2 tiles per hi block
+    const unsigned long long hi = tile >> tph;
+    g.k0 = (tile & ((1ull << tph) - 1)) << p.log_t;
+    g.gbase = g.k0 + (hi << (p.log_m + p.r));
+    g.rowshift = p.log_m;
+  }
+
+  // ---- load: 16-byte pieces, columns fastest (256 B contiguous per row) ----
+  for (int idx = threadIdx.x; idx < elems * PIECES; idx += blockDim.x) {
+    const int piece = idx % PIECES;
+    const int e = idx / PIECES;
+    const int col = e & (T - 1);
+    const int row = e >> p.log_t;
+    const unsigned long long gidx = g.gbase + col + ((unsigned long long)row << g.rowshift);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (!p.first || gidx < p.n_in) v = in[gidx * PIECES + piece];
+    const int srow = (int)bitrev((unsigned)row, p.r);
+    smem[piece * elems + srow * T + (col ^ (srow & (T - 1)))] = v;
+  }
+  __syncthreads();
+
+  // ---- input-side factors, then butterflies as radix-8 / 4 / 2 register rounds ----
+  if ((p.first && p.pre_lo) || !p.first || p.scale) ntt_pre_factors<F>(p, g, smem);
+  {
+    int l0 = 0;
+    const int r = p.r;
+    if (r >= 3) { ntt_round<F, 3, true>(p, smem, 0); l0 = 3; }
+    else if (r == 2) { ntt_round<F, 2, true>(p, smem, 0); l0 = 2; }
+    else if (r == 1) { ntt_round<F, 1, true>(p, smem, 0); l0 = 1; }
+    while (l0 < r) {
+      const int q = (r - l0 >= 3) ? 3 : (r - l0);
+      if (q == 3) ntt_round<F, 3, false>(p, smem, l0);
+      else if (q == 2) ntt_round<F, 2, false>(p, smem, l0);
+      else ntt_round<F, 1, false>(p, smem, l0);
+      l0 += q;
+    }
+  }
+  if (p.last && (p.post_lo || p.post_periodic)) ntt_post_factors<F>(p, g, smem);
+
+  // ---- store ----
+  if (!p.first) {
+    for (int idx = threadIdx.x; idx < elems * PIECES; idx += blockDim.x) {
+      const int piece = idx % PIECES;
+      const int e = idx / PIECES;
+      const int col = e & (T - 1);
+      const int row = e >> p.log_t;
+      const unsigned long long gidx = g.gbase + col + ((unsigned long long)row << g.rowshift);
+      out[gidx * PIECES + piece] = smem[piece * elems + row * T + (col ^ (row & (T - 1)))];
+    }
+  } else {
+    // column c of the tile becomes a run of R contiguous outputs at rev_digits(jlow) * R
+    for (int idx = threadIdx.x; idx < elems * PIECES; idx += blockDim.x) {
+      const int piece = idx % PIECES;
+      const int e = idx / PIECES;
+      const int row = e & (R - 1);
+      const int col = e >> p.r;
+      unsigned long long x = g.k0 + col, pos = 0;
+      for (int i = 0; i < p.ndig; ++i) {
+        pos = (pos << p.digs[i]) | (x & ((1ull << p.digs[i]) - 1));
+        x >>= p.digs[i];
+      }
+      const unsigned long long gidx = (pos << p.r) + row;
+      out[gidx * PIECES + piece] = smem[piece * elems + row * T + (col ^ (row & (T - 1)))];
+    }
+  }
+}
+
+// out[i] = base^(i * stride) for i < count (64-bit exponents), optionally times `scale`
+template <class F>
+__global__ void pow_table_kernel(F base, unsigned long long stride_log2, unsigned long long count, const F* scale, F* out) {
+  unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  // base^(i << stride_log2): square the base stride_log2 times first (uniform), then binary powering
+  F b = base;
+  for (unsigned long long s = 0; s < stride_log2; ++s) b = F::sqr(b);
+  F acc = F::one();
+  unsigned long long e = i;
+  while (e) {
+    if (e & 1) acc = F::mul(acc, b);
+    b = F::sqr(b);
+    e >>= 1;
+  }
+  if (scale) acc = F::mul(acc, *scale);
+  out[i] = acc;
+}
+
+// denominators of divide_by_z_h (src/polynomial.rs:351-361): tbl[i] = 1 / (g^n * w^(n i) - 1), i < period
+template <class F>
+__global__ void zh_inverse_table_kernel(F gn, F wn, unsigned count, F* out, int* zero_flag) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  F acc = F::one(), b = wn;
+  unsigned e = i;
+  while (e) {
+    if (e & 1) acc = F::mul(acc, b);
+    b = F::sqr(b);
+    e >>= 1;
+  }
+  F d = F::sub(F::mul(gn, acc), F::one());
+  if (d.is_zero()) { *zero_flag = 1; out[i] = d; return; }
+  out[i] = F::inverse(d);
+}
+
+}  // namespace plk

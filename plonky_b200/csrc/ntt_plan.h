@@ -1,0 +1,64 @@
+// Host-side plan structures of the NTT (shared by the per-field kernel translation units and the C ABI).
+#pragma once
+#include <map>
+#include <mutex>
+#include <vector>
+#include "common.cuh"
+
+namespace plk {
+constexpr int kSubLog = 8;          // largest sub-transform: 2^8 rows
+constexpr int kMaxDigits = 6;       // 6 * 8 = 48 >= largest TWO_ADICITY (47)
+constexpr int kTileColsLog = 3;     // 8 columns per tile
+constexpr int kNttThreads = 256;
+}  // namespace plk
+
+struct CosetTables {
+  plk::DevBuf fwd_lo, fwd_hi;    // s^j
+  plk::DevBuf inv_lo, inv_hi;    // s^-j
+};
+
+struct plk_fft_plan {
+  int field = 0;
+  int log_n = 0;
+  size_t n = 0;
+  int device = 0;
+  int m = 0;                 // passes
+  int dig[plk::kMaxDigits];       // r_1 .. r_m
+  int lo_bits = 0;
+  size_t elem_bytes = 32;
+  plk::DevBuf wsub[2];            // [0] forward, [1] inverse
+  plk::DevBuf tw_lo[2], tw_hi[2];
+  plk::DevBuf tw_hi_inv_scaled;   // inverse hi table with n^-1 folded in
+  plk::DevBuf n_inv;              // one element: n^-1
+  std::mutex mu;
+  std::map<std::vector<uint32_t>, CosetTables*> cosets;   // keyed by the shift's limbs
+  std::map<size_t, plk::DevBuf*> zh_tables;                     // keyed by n_gates
+  // scratch for the host-pointer entry points
+  plk::DevBuf h_in, h_out;
+  ~plk_fft_plan() {
+    for (auto& kv : cosets) delete kv.second;
+    for (auto& kv : zh_tables) delete kv.second;
+  }
+};
+
+
+namespace plk {
+struct FusedOps {
+  const void* pre_lo = nullptr;
+  const void* pre_hi = nullptr;
+  const void* post_lo = nullptr;
+  const void* post_hi = nullptr;
+  const void* post_periodic = nullptr;
+  unsigned long long post_mask = 0;
+};
+
+
+// per-field entry points (one translation unit per field keeps ptxas time parallel)
+struct NttOps {
+  void (*plan_build)(plk_fft_plan*);
+  void (*run)(const plk_fft_plan*, const void* d_in, size_t n_in, size_t in_stride, void* d_out, size_t k, bool inverse,
+              const FusedOps* ops, cudaStream_t st);
+  void (*coset)(plk_fft_plan*, const uint64_t* shift, bool inverse, FusedOps* ops, cudaStream_t st);
+  void (*zh_table)(plk_fft_plan*, size_t n_gates, FusedOps* ops, cudaStream_t st);
+};
+}  // namespace plk
