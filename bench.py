@@ -1,0 +1,421 @@
+#!/usr/bin/env python3
+"""bench.py -- the hot path of plonky on B200: Tweedledee G1 MSM 2^20 (headline) + TweedledeeBase NTT 2^24.
+
+Contract (one JSON line on rank 0):
+  python bench.py --gpus N --steps K --warmup W            our CUDA path
+  python bench.py --impl reference --gpus N ...            the reference's CPU algorithm on the host cores
+      (the reference is Rust and cannot be built in this image: this arm times the C++ restatement of
+       its algorithms, oracle/ref_port.cpp, kind = "port")
+
+A "step" is one msm_execute of 2^20 scalars against a fixed-base table built once (the prover's usage:
+18 MSMs per proof against pedersen_g, src/plonk.rs:100-235, timed like src/bin/msms.rs:25,47-60).
+  value   scalar-muls/s, whole job, inputs resident in HBM, CUDA events on the launching stream
+  e2e     the same through the C ABI with HOST (pinned) buffers: H2D of the scalars + D2H of the point
+  roofline  dominant kernel (bucket accumulation): algorithmic bytes (96 B / term) / its launch time
+  ntt     secondary object: NTT 2^24 elements/s, coset LDE 2^21 -> 2^24, their roofline and e2e
+Multi-GPU (torchrun, one rank per GPU): weak scaling -- every rank owns its own 2^20-term shard of an
+N * 2^20-term MSM; one all-gather of the 128-byte partials per step (NCCL), then every rank combines.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MSM_LOG_N = 20
+NTT_LOG_N = 24
+LDE_LOG_IN = 21
+CURVE = 0            # Tweedledee
+NTT_FIELD = 0        # TweedledeeBase (benches/fft.rs:8)
+SEED = 0x504C4B59
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        top = sorted(sm)[len(sm) // 2:]          # the loaded half of the samples
+        return {"sm_mhz": statistics.median(top), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def rand_scalars_np(n, seed):
+    """n random field elements (as Montgomery limb patterns): 4 x u64, top limb < 2^62 => value < 2^254 < q."""
+    import numpy as np
+    rng = np.random.Generator(np.random.PCG64(seed))
+    a = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, 4), dtype=np.uint64)
+    a[:, 3] >>= np.uint64(2)
+    return a
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the C++ restatement of the reference algorithm on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_port_lib():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_port as rp
+    try:                      # -march=native on the box that runs it (mirrors .cargo/config:2)
+        rp.build(native=True)
+        return rp, rp.lib(native=True), "native"
+    except Exception:
+        return rp, rp.lib(), "x86-64-v3"
+
+
+def cpu_msm_baseline(budget_s=12.0, log_n=14, steps=None, warmup=1):
+    """msm_execute_parallel (curve_msm.rs:102-157) restated in C++/OpenMP: w = 11, all host threads, on a
+    bounded sample of the workload (2^log_n terms of the same distribution; table built once, untimed)."""
+    import numpy as np
+    rp, L, march = cpu_port_lib()
+    cores = os.cpu_count() or 1
+    L.ref_set_threads(cores)
+    n = 1 << log_n
+    xy = rp.gen_points(CURVE, SEED + 1, n, L)
+    t0 = time.perf_counter()
+    table = rp.MsmTable(CURVE, xy, None, 11, L)
+    pre_s = time.perf_counter() - t0
+    s = rand_scalars_np(n, SEED + 2)
+    times = []
+    for _ in range(warmup):
+        table.execute(s, parallel=True)
+    t_start = time.perf_counter()
+    while True:
+        t0 = time.perf_counter()
+        table.execute(s, parallel=True)
+        times.append(time.perf_counter() - t0)
+        if steps is not None and len(times) >= steps:
+            break
+        if steps is None and (time.perf_counter() - t_start > budget_s or len(times) >= 20):
+            break
+    best = statistics.median(times)
+    return {"value": n / best, "unit": "scalar-muls/s", "cores": cores, "kind": "port",
+            "sample": f"Tweedledee MSM 2^{log_n} terms, w=11, msm_execute_parallel restated in C++/OpenMP ({march}), "
+                      f"median of {len(times)} runs, table precompute {pre_s:.1f}s untimed",
+            "ms_per_step": best * 1e3}
+
+
+def cpu_ntt_baseline(log_n=20, reps=3):
+    import numpy as np
+    rp, L, march = cpu_port_lib()
+    cores = os.cpu_count() or 1
+    L.ref_set_threads(cores)
+    n = 1 << log_n
+    x = rand_scalars_np(n, SEED + 3)
+    plan = rp.FftPlan(NTT_FIELD, n, L)
+    plan.run(x)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        plan.run(x)
+        times.append(time.perf_counter() - t0)
+    best = statistics.median(times)
+    return {"value": n / best, "unit": "elements/s", "cores": cores, "kind": "port",
+            "sample": f"TweedledeeBase NTT 2^{log_n}, fft_with_precomputation_power_of_2 restated in C++/OpenMP ({march}), median of {reps}"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    base = cpu_msm_baseline(log_n=14, steps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference",
+        "metric": "msm_scalar_muls_per_sec", "value": base["value"], "unit": "scalar-muls/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64x4 (Montgomery, 255-bit)",
+        "data": "synthetic",
+        "config": {"workload": "Tweedledee G1 MSM 2^20 (fixed-base table, execute only); this arm: bounded 2^14-term sample per step on host cores"},
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": "scalar-muls/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import plonky_b200 as pk
+    from plonky_b200 import distributed as pkd
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    pk._check(pk.lib().plk_set_device(local))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    hbm_peak, peak_kind = peaks()
+    K, W = args.steps, max(3, args.warmup)
+    n = 1 << args.msm_log_n
+
+    # ---- setup (untimed): synthetic generators on device, fixed-base table, scalar buffers ----
+    pts = pkd.points_generate_dev(CURVE, SEED + 1 + rank * n, n)
+    table = pkd.msm_precompute_affine_dev(CURVE, pts, 11)
+    del pts
+    NBUF = 4                                  # rotate inputs; the 1 GiB table walk alone exceeds L2 (126 MB)
+    host_scalars = [torch.from_numpy(rand_scalars_np(n, SEED + 100 * rank + i).view(np.int64)).pin_memory() for i in range(NBUF)]
+    dev_scalars = [h.cuda(non_blocking=True) for h in host_scalars]
+    Lb = 4
+    out_xyz = torch.zeros((3, Lb), dtype=torch.int64, device="cuda")
+    out_zero = torch.zeros(8, dtype=torch.uint8, device="cuda")
+    partial = torch.zeros(4 * Lb, dtype=torch.int64, device="cuda")
+    gathered = torch.zeros(world * 4 * Lb, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+
+    def step(i):
+        pkd.msm_execute_sharded(table, dev_scalars[i % NBUF], partial, gathered, out_xyz, out_zero)
+
+    # ---- value: device-resident, CUDA events on the launching (current) stream ----
+    for i in range(W):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = pk.kernel_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(K):
+        step(i)
+    ev1.record()
+    barrier()
+    launches = pk.kernel_launch_count() - launches0
+    ms_step = max_over_ranks(ev0.elapsed_time(ev1) / K)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * n / (ms_step * 1e-3)
+
+    # ---- per-kernel times (same inputs, same process, right after the timed steps) ----
+    pk.set_profiling(True)
+    phase_acc = None
+    PK = min(K, 10)
+    for i in range(PK):
+        step(i)
+        ph = pk.msm_last_phase_ms(table)
+        phase_acc = ph if phase_acc is None else [a + b for a, b in zip(phase_acc, ph)]
+    pk.set_profiling(False)
+    phases = {name: t / PK for name, t in zip(pk.MSM_PHASES, phase_acc or [])}
+    acc_ms = phases.get("accumulate", float("nan"))
+    alg_bytes = n * 96                                  # 32 B scalar + 64 B affine point per term
+    achieved = alg_bytes / (acc_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "msm_accumulate_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_kind": peak_kind,
+                "kernel_ms": acc_ms, "kernel_share_of_step": acc_ms / sum(phases.values()) if phases else None,
+                "phases_ms": phases,
+                "note": "integer-ALU bound (IMAD.WIDE chains), not HBM bound: see DESIGN.md; table walk reads nwin*64 B per term"}
+
+    # ---- e2e: the C-ABI host call with pinned host scalars (H2D + D2H inside the timed region) ----
+    out_h = np.zeros((3, Lb), dtype=np.uint64)
+    oz_h = np.zeros(1, dtype=np.uint8)
+    L = pk.lib()
+    u64p = C.POINTER(C.c_uint64)
+
+    def e2e_step(i):
+        if world == 1:
+            hs = host_scalars[i % NBUF]
+            pk._check(L.plk_msm_execute(table.handle, C.cast(hs.data_ptr(), u64p), n,
+                                        out_h.ctypes.data_as(u64p), oz_h.ctypes.data_as(C.POINTER(C.c_uint8))))
+        else:
+            d = dev_scalars[i % NBUF]
+            d.copy_(host_scalars[i % NBUF], non_blocking=True)
+            pkd.msm_execute_sharded(table, d, partial, gathered, out_xyz, out_zero)
+            out_xyz.cpu()
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        e2e_step(i)
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / K)
+    e2e = {"value": world * n / (e2e_ms * 1e-3), "unit": "scalar-muls/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 3 * Lb * 8 + 1,
+           "ms_per_step": e2e_ms}
+
+    line = {
+        "metric": "msm_scalar_muls_per_sec", "value": value, "unit": "scalar-muls/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64x4 (Montgomery, 255-bit)", "data": "synthetic",
+        "config": {"workload": f"Tweedledee G1 MSM 2^{args.msm_log_n} per GPU, fixed-base table (msm_precompute once, execute timed)",
+                   "terms_per_gpu": n, "total_terms": world * n, "window_passed": 11,
+                   "l2": "inputs larger than L2: 1 GiB table walk per step + 4 rotating 32 MiB scalar vectors",
+                   "multi_gpu": "shard per rank, all-gather of 128 B partials, combine on every rank" if world > 1 else "single GPU"},
+        "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+
+    # ---- secondary: NTT 2^24 + coset LDE (rank 0 at N = 1 only keeps the default run short) ----
+    if world == 1 and not args.skip_ntt:
+        line["ntt"] = bench_ntt(args, pk, pkd, torch, np, hbm_peak, peak_kind)
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        line["cpu_baseline"] = {k: v for k, v in cpu_msm_baseline(budget_s=12.0, log_n=14).items() if k != "ms_per_step"}
+        if "ntt" in line:
+            line["ntt"]["cpu_baseline"] = cpu_ntt_baseline(log_n=20)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def bench_ntt(args, pk, pkd, torch, np, hbm_peak, peak_kind):
+    K, W = args.steps, max(3, args.warmup)
+    n = 1 << args.ntt_log_n
+    plan = pk.fft_precompute(NTT_FIELD, n)
+    host_in = torch.from_numpy(rand_scalars_np(n, SEED + 7).view(np.int64)).pin_memory()
+    d_in = host_in.cuda()
+    d_out = torch.empty_like(d_in)
+    torch.cuda.synchronize()
+
+    def timed(fn):
+        for _ in range(W):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / K
+
+    l0 = pk.kernel_launch_count()
+    fwd_ms = timed(lambda: pkd.fft_dev(plan, d_in, d_out))
+    launches = (pk.kernel_launch_count() - l0) // (K + W)
+    inv_ms = timed(lambda: pkd.fft_dev(plan, d_in, d_out, inverse=True))
+    m = 1 << (args.ntt_log_n - (NTT_LOG_N - LDE_LOG_IN))
+    lde_ms = timed(lambda: pkd.fft_dev(plan, d_in[:m], d_out, coset=True))
+    pk.set_profiling(True)
+    passes = None
+    for _ in range(5):
+        pkd.fft_dev(plan, d_in, d_out)
+        p = pk.fft_last_pass_ms(plan)
+        passes = p if passes is None else [a + b for a, b in zip(passes, p)]
+    pk.set_profiling(False)
+    passes = [p / 5 for p in passes]
+    alg = 2 * n * 32
+    achieved = alg / (sum(passes) * 1e-3) / 1e9
+    # e2e through the C ABI with pinned host buffers
+    host_out = torch.empty_like(host_in).pin_memory()
+    u64p = C.POINTER(C.c_uint64)
+    L = pk.lib()
+
+    def e2e():
+        pk._check(L.plk_fft_pow2(plan.handle, C.cast(host_in.data_ptr(), u64p), C.cast(host_out.data_ptr(), u64p), n))
+    e2e()
+    t0 = time.perf_counter()
+    reps = max(2, min(K, 5))
+    for _ in range(reps):
+        e2e()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / reps
+    return {
+        "metric": "ntt_elements_per_sec", "value": n / (fwd_ms * 1e-3), "unit": "elements/s", "ms_per_step": fwd_ms,
+        "config": {"workload": f"TweedledeeBase radix-2 NTT 2^{args.ntt_log_n}, natural order in/out, device resident",
+                   "l2": "input + output = 1 GiB > L2"},
+        "inverse_ms": inv_ms, "coset_lde_ms": lde_ms, "coset_lde": f"2^{args.ntt_log_n - 3} coefficients -> 2^{args.ntt_log_n} evaluations on g*H, fused shift + zero-pad",
+        "coset_lde_elements_per_sec": n / (lde_ms * 1e-3),
+        "launches_per_transform": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "ntt_pass_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": achieved / hbm_peak, "traffic": None, "peak_kind": peak_kind, "pass_ms": passes,
+                     "note": "algorithmic bytes 2*n*32 over the sum of the pass launches; the 3-pass design moves 3x that; ALU bound"},
+        "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "elements/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": n * 32,
+                "ms_per_step": e2e_ms},
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--msm-log-n", type=int, default=MSM_LOG_N)
+    ap.add_argument("--ntt-log-n", type=int, default=NTT_LOG_N)
+    ap.add_argument("--skip-ntt", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

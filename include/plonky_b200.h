@@ -185,6 +185,15 @@ int plk_msm_precompute_affine_dev(int curve, const void* d_points_xy, size_t n, 
 /* number of CUDA kernels this library has launched in the calling process (bench.py: gpu_launches) */
 uint64_t plk_kernel_launch_count(void);
 
+/* Measurement hooks (bench.py's live roofline numbers).  With profiling enabled every MSM execute /
+ * transform records CUDA events between its kernels on the launching stream; the *_last_*_ms calls
+ * synchronise on the last event and return the number of phases written (negative status on error).
+ * MSM phases: count, scan, scatter, accumulate, bucket_sum, range, final.  NTT: one phase per pass. */
+int plk_set_profiling(int enabled);
+int plk_msm_last_phase_ms(const plk_msm_table* t, float* out_ms, int cap);
+int plk_fft_last_pass_ms(const plk_fft_plan* p, float* out_ms, int cap);
+int plk_fft_num_passes(const plk_fft_plan* p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -115,6 +115,10 @@ def lib():
     L.plk_points_generate_dev.argtypes = [C.c_int, C.c_uint64, sz, vp, vp]
     L.plk_points_generate.argtypes = [C.c_int, C.c_uint64, sz, u64p]
     L.plk_kernel_launch_count.restype = C.c_uint64
+    L.plk_set_profiling.argtypes = [C.c_int]
+    L.plk_msm_last_phase_ms.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
+    L.plk_fft_last_pass_ms.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
+    L.plk_fft_num_passes.argtypes = [vp]
     _LIB = L
     return L
 
@@ -153,6 +157,26 @@ def _zero_flags(zero, n) -> Optional[np.ndarray]:
 
 def kernel_launch_count() -> int:
     return int(lib().plk_kernel_launch_count())
+
+
+MSM_PHASES = ("count", "scan", "scatter", "accumulate", "bucket_sum", "range", "final")
+
+
+def set_profiling(enabled: bool):
+    """Record CUDA events between the kernels of every MSM execute / transform (measurement only)."""
+    lib().plk_set_profiling(1 if enabled else 0)
+
+
+def msm_last_phase_ms(pre: "MsmPrecomputation"):
+    buf = (C.c_float * 12)()
+    n = lib().plk_msm_last_phase_ms(pre.handle, buf, 12)
+    return [float(buf[i]) for i in range(max(n, 0))]
+
+
+def fft_last_pass_ms(pre: "FftPrecomputation"):
+    buf = (C.c_float * 12)()
+    n = lib().plk_fft_last_pass_ms(pre.handle, buf, 12)
+    return [float(buf[i]) for i in range(max(n, 0))]
 
 
 # ------------------------------------------------------------------------------------------------

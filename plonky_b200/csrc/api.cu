@@ -7,6 +7,7 @@
 namespace plk {
 
 std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_profiling{0};
 
 static thread_local std::string t_last_error;
 void set_last_error(const std::string& s) { t_last_error = s; }
@@ -182,6 +183,7 @@ int plk_curve_scalar_field(int curve) {
   return -1;
 }
 uint64_t plk_kernel_launch_count(void) { return g_launches.load(); }
+int plk_set_profiling(int enabled) { g_profiling.store(enabled ? 1 : 0); return PLK_OK; }
 
 int plk_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
   return guarded([&] {

@@ -12,6 +12,7 @@
 namespace plk {
 
 extern std::atomic<uint64_t> g_launches;
+extern std::atomic<int> g_profiling;     // plk_set_profiling: record CUDA events between pipeline phases
 void set_last_error(const std::string& s);
 
 struct CudaError {
@@ -93,6 +94,34 @@ struct DevBuf {
   void ensure(size_t b) { if (b > bytes) alloc(b); }
   void release() { if (p) { cudaFree(p); p = nullptr; bytes = 0; } }
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Phase timer: CUDA events recorded on the launching stream between the kernels of one call (only when
+// profiling is enabled; bench.py uses it for the live per-kernel roofline numbers).
+struct PhaseTimer {
+  static constexpr int kMax = 12;
+  cudaEvent_t ev[kMax + 1];
+  int n = 0;        // events recorded in the last call
+  bool created = false;
+  void begin(cudaStream_t st) {
+    if (!g_profiling.load(std::memory_order_relaxed)) { n = 0; return; }
+    if (!created) { for (auto& e : ev) PLK_CUDA(cudaEventCreate(&e)); created = true; }
+    n = 0;
+    mark(st);
+  }
+  void mark(cudaStream_t st) {
+    if (!created || !g_profiling.load(std::memory_order_relaxed) || n > kMax) return;
+    PLK_CUDA(cudaEventRecord(ev[n++], st));
+  }
+  // elapsed ms of each phase of the last call; returns the number of phases
+  int read(float* out, int cap) {
+    if (n < 2) return 0;
+    PLK_CUDA(cudaEventSynchronize(ev[n - 1]));
+    int k = 0;
+    for (int i = 0; i + 1 < n && k < cap; ++i, ++k) PLK_CUDA(cudaEventElapsedTime(&out[k], ev[i], ev[i + 1]));
+    return k;
+  }
+  ~PhaseTimer() { if (created) for (auto& e : ev) cudaEventDestroy(e); }
 };
 
 inline bool is_pow2(size_t n) { return n != 0 && (n & (n - 1)) == 0; }

@@ -199,6 +199,15 @@ int plk_msm_combine_partials_dev(int curve, const void* d_partials, size_t count
     ops_for(curve)->combine_partials(d_partials, count, d_out_xyz, d_out_zero, reinterpret_cast<cudaStream_t>(stream));
   });
 }
+int plk_msm_last_phase_ms(const plk_msm_table* tc, float* out_ms, int cap) {
+  int n = 0;
+  int rc = guarded([&] {
+    auto* t = const_cast<plk_msm_table*>(tc);
+    if (!t || !out_ms) fail(PLK_EINVAL, "bad arguments");
+    n = t->timer.read(out_ms, cap);
+  });
+  return rc == PLK_OK ? n : -rc;
+}
 size_t plk_msm_partial_limbs(int curve) { return 4 * (size_t)curve_base_limbs64(curve); }
 
 int plk_points_generate_dev(int curve, uint64_t seed, size_t n, void* d_points_xy, void* stream) {

@@ -364,28 +364,36 @@ void execute_one(plk_msm_table* t, const void* d_scalars, void* d_out_xyz, void*
     return;
   }
   PLK_CUDA(cudaMemsetAsync(t->counts.p, 0, (size_t)g.nb * 4, st));
+  t->timer.begin(st);
   const unsigned sblocks = (unsigned)((g.n + 255) / 256);
   msm_count_kernel<C><<<sblocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(d_scalars), g, t->counts.as<unsigned>());
   PLK_LAUNCHED();
+  t->timer.mark(st);
   msm_scan_kernel<<<1, 1024, 0, st>>>(t->counts.as<unsigned>(), g.nb, t->offsets.as<unsigned>(), t->task_off.as<unsigned>(),
                                       t->cursors.as<unsigned>());
   PLK_LAUNCHED();
+  t->timer.mark(st);
   msm_scatter_kernel<C><<<sblocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(d_scalars), g, t->cursors.as<unsigned>(),
                                                  t->sorted.as<unsigned>());
   PLK_LAUNCHED();
+  t->timer.mark(st);
   const unsigned ablocks = (unsigned)((t->max_tasks + kAccThreads - 1) / kAccThreads);
   msm_accumulate_kernel<C><<<ablocks, kAccThreads, 0, st>>>(t->table.p, t->sorted.as<unsigned>(), t->offsets.as<unsigned>(),
                                                             t->task_off.as<unsigned>(), g.nb, t->partials.p);
   PLK_LAUNCHED();
+  t->timer.mark(st);
   msm_bucket_sum_kernel<C><<<(g.nb + 127) / 128, 128, 0, st>>>(t->partials.p, t->task_off.as<unsigned>(), g.nb, t->buckets.p);
   PLK_LAUNCHED();
+  t->timer.mark(st);
   const unsigned nranges = (g.nb + kRangeSize - 1) / kRangeSize;
   msm_range_kernel<C><<<(nranges + 63) / 64, 64, 0, st>>>(t->buckets.p, g.nb, t->ranges.p);
   PLK_LAUNCHED();
+  t->timer.mark(st);
   const unsigned fthreads = nranges >= 256 ? 256 : (nranges >= 32 ? 32 : 1);
   msm_final_kernel<C><<<1, fthreads, fthreads * xyzz, st>>>(t->ranges.p, nranges, d_partial, reinterpret_cast<uint32_t*>(d_out_xyz),
                                                             reinterpret_cast<unsigned char*>(d_out_zero));
   PLK_LAUNCHED();
+  t->timer.mark(st);
 }
 
 template <class C>

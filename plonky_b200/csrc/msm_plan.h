@@ -28,6 +28,7 @@ struct plk_msm_table {
   std::mutex mu;
   plk::DevBuf counts, offsets, task_off, cursors, sorted, partials, buckets, ranges, result;
   size_t max_tasks = 0;
+  plk::PhaseTimer timer;   // count | scan | scatter | accumulate | bucket_sum | range | final
 };
 
 

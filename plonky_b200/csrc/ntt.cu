@@ -79,6 +79,16 @@ int plk_fft_precompute(int field, size_t degree, plk_fft_plan** out) {
 }
 
 size_t plk_fft_size(const plk_fft_plan* p) { return p ? p->n : 0; }
+int plk_fft_num_passes(const plk_fft_plan* p) { return p ? p->m : 0; }
+int plk_fft_last_pass_ms(const plk_fft_plan* pc, float* out_ms, int cap) {
+  int n = 0;
+  int rc = guarded([&] {
+    auto* p = const_cast<plk_fft_plan*>(pc);
+    if (!p || !out_ms) fail(PLK_EINVAL, "bad arguments");
+    n = p->timer.read(out_ms, cap);
+  });
+  return rc == PLK_OK ? n : -rc;
+}
 
 void plk_fft_free(plk_fft_plan* p) { delete p; }
 

@@ -69,6 +69,8 @@ void run_ntt(const plk_fft_plan* pl, const void* d_in, size_t n_in, size_t in_st
     attr_set[dev & 7] = true;
   }
   int log_m_acc = 0;   // log2 of M_d for the pass being issued
+  PhaseTimer& timer = const_cast<plk_fft_plan*>(pl)->timer;
+  timer.begin(st);
   for (int pass = 0; pass < m; ++pass) {
     const int d = m - 1 - pass;          // digit index (0-based): pass 0 handles r_m
     NttPassParams p;
@@ -110,6 +112,7 @@ void run_ntt(const plk_fft_plan* pl, const void* d_in, size_t n_in, size_t in_st
     dim3 grid((unsigned)tiles, (unsigned)k);
     ntt_pass_kernel<F><<<grid, kNttThreads, smem, st>>>(p);
     PLK_LAUNCHED();
+    timer.mark(st);
     log_m_acc += p.r;
   }
 }

@@ -33,8 +33,7 @@ struct plk_fft_plan {
   std::mutex mu;
   std::map<std::vector<uint32_t>, CosetTables*> cosets;   // keyed by the shift's limbs
   std::map<size_t, plk::DevBuf*> zh_tables;                     // keyed by n_gates
-  // scratch for the host-pointer entry points
-  plk::DevBuf h_in, h_out;
+  plk::PhaseTimer timer;          // one phase per pass of the last transform
   ~plk_fft_plan() {
     for (auto& kv : cosets) delete kv.second;
     for (auto& kv : zh_tables) delete kv.second;
