@@ -164,6 +164,21 @@ int plk_divide_by_z_h(const plk_fft_plan* p, const uint64_t* coeffs, size_t n_in
 int plk_fft_dev(const plk_fft_plan* p, const void* d_in, size_t n_in, size_t k, unsigned flags,
                 void* d_out, void* stream);
 
+/* Domain-split transform of size N = R1 * M over `world` GPUs (one process per GPU; the caller performs
+ * the single all-to-all between the phases, e.g. torch.distributed.all_to_all_single over NCCL):
+ *   layout in : rank r holds rows j_1 in [row_base, row_base + rows) of x[j_1 + R1 * j'], each of length M
+ *   phase A   : size-M transforms (plan_m) * w_N^(j_1 k') -> d_send in the send layout
+ *               [dest][row][k' mod (M / world)]; d_work is an M * rows element work buffer
+ *   exchange  : all-to-all with equal splits
+ *   phase B   : in place on the received buffer [j_1][M / world]: transform over j_1 (R1 = 2^log_r1 <= 256)
+ *   layout out: rank s holds X[k' + M * k_1] at [k_1][kl], k' = s * M / world + kl
+ * flags: PLK_FFT_INVERSE.  plan_n is the plan of size N (its twiddle tables are used), plan_m of size M. */
+int plk_fft_dist_phase_a(const plk_fft_plan* plan_m, const plk_fft_plan* plan_n, const void* d_in,
+                         size_t rows, size_t row_base, unsigned world, unsigned flags, void* d_work,
+                         void* d_send, void* stream);
+int plk_fft_dist_phase_b(const plk_fft_plan* plan_n, void* d_recv, unsigned log_r1, unsigned log_cols,
+                         unsigned flags, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Helpers on the same arithmetic (used by the parity tests and by callers that stay on device)
  * ---------------------------------------------------------------------------------------- */
@@ -175,6 +190,17 @@ int plk_batch_inverse(int field, const uint64_t* in, uint64_t* out, size_t n);
 /* ProjectivePoint::batch_to_affine (src/curve/curve.rs:216-232) */
 int plk_batch_to_affine(int curve, const uint64_t* points_xyz, const uint8_t* zero, size_t n,
                         uint64_t* out_xy, uint8_t* out_zero);
+/* affine_summation_best / affine_multisummation_best (src/curve/curve_summations.rs:18-35): sums of affine
+ * points; `lists` lists are the slices [offsets[i], offsets[i+1]) of points_xy.  Results are normalised
+ * projective points (3*L limbs each) + zero flags.  An empty list sums to ZERO (curve_summations.rs:170). */
+int plk_affine_summation(int curve, const uint64_t* points_xy, const uint8_t* zero, size_t n,
+                         uint64_t* out_xyz, uint8_t* out_zero);
+int plk_affine_multisummation(int curve, const uint64_t* points_xy, const uint8_t* zero,
+                              const uint64_t* offsets, size_t lists, uint64_t* out_xyz, uint8_t* out_zero);
+/* n independent CurveScalar * ProjectivePoint products (src/curve/curve_multiplication.rs:63-70), e.g. the
+ * blinding terms of PolynomialCommitment::coeffs_to_commitment (src/poly_commit.rs:44). */
+int plk_curve_mul(int curve, const uint64_t* points_xyz, const uint8_t* zero, const uint64_t* scalars,
+                  size_t n, uint64_t* out_xyz, uint8_t* out_zero);
 /* Synthetic generator set for benchmarks: P_i = [splitmix64(seed + i)] * G, affine, written to device
  * (d_points_xy: n*2*L u64).  Stands in for blake_hash_usize_to_curve (src/hash_to_curve.rs:53-76). */
 int plk_points_generate_dev(int curve, uint64_t seed, size_t n, void* d_points_xy, void* stream);

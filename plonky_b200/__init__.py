@@ -33,7 +33,7 @@ __all__ = [
     "msm_execute_batch", "msm_parallel", "pedersen_hash",
     "FftPrecomputation", "fft_precompute", "fft", "fft_with_precomputation", "fft_with_precomputation_power_of_2",
     "ifft_with_precomputation_power_of_2", "fft_batch", "coset_lde", "coset_ifft", "divide_by_z_h",
-    "field_op", "batch_multiplicative_inverse", "batch_to_affine", "points_generate", "kernel_launch_count",
+    "field_op", "batch_multiplicative_inverse", "batch_to_affine", "affine_summation_best", "affine_multisummation_best", "curve_mul", "points_generate", "kernel_launch_count",
 ]
 
 # ids of include/plonky_b200.h
@@ -109,9 +109,14 @@ def lib():
     L.plk_coset_ifft.argtypes = [vp, u64p, u64p, u64p]
     L.plk_divide_by_z_h.argtypes = [vp, u64p, sz, sz, u64p]
     L.plk_fft_dev.argtypes = [vp, vp, sz, sz, C.c_uint, vp, vp]
+    L.plk_fft_dist_phase_a.argtypes = [vp, vp, vp, sz, sz, C.c_uint, C.c_uint, vp, vp, vp]
+    L.plk_fft_dist_phase_b.argtypes = [vp, vp, C.c_uint, C.c_uint, C.c_uint, vp]
     L.plk_field_op.argtypes = [C.c_int, C.c_int, u64p, u64p, u64p, sz]
     L.plk_batch_inverse.argtypes = [C.c_int, u64p, u64p, sz]
     L.plk_batch_to_affine.argtypes = [C.c_int, u64p, u8p, sz, u64p, u8p]
+    L.plk_affine_summation.argtypes = [C.c_int, u64p, u8p, sz, u64p, u8p]
+    L.plk_affine_multisummation.argtypes = [C.c_int, u64p, u8p, u64p, sz, u64p, u8p]
+    L.plk_curve_mul.argtypes = [C.c_int, u64p, u8p, u64p, sz, u64p, u8p]
     L.plk_points_generate_dev.argtypes = [C.c_int, C.c_uint64, sz, vp, vp]
     L.plk_points_generate.argtypes = [C.c_int, C.c_uint64, sz, u64p]
     L.plk_kernel_launch_count.restype = C.c_uint64
@@ -419,6 +424,45 @@ def batch_to_affine(curve: int, points_xyz, zero=None):
     out = np.zeros((n, 2, Lb), dtype=np.uint64)
     oz = np.zeros(n, dtype=np.uint8)
     _check(lib().plk_batch_to_affine(curve, _p64(g), _p8(z), n, _p64(out), _p8(oz)))
+    return out, oz
+
+
+def affine_multisummation_best(curve: int, summations, zeros=None):
+    """affine_multisummation_best(summations: Vec<Vec<AffinePoint>>) (src/curve/curve_summations.rs:24-35):
+    a list of (n_i, 2, L) arrays -> (k, 3, L) normalised projective sums + zero flags."""
+    Lb = FIELD_LIMBS[CURVE_BASE_FIELD[curve]]
+    lists = [_u64(s).reshape(-1, 2, Lb) for s in summations]
+    k = len(lists)
+    offsets = np.zeros(k + 1, dtype=np.uint64)
+    for i, l in enumerate(lists):
+        offsets[i + 1] = offsets[i] + np.uint64(l.shape[0])
+    pts = np.concatenate(lists) if k and int(offsets[-1]) else np.zeros((0, 2, Lb), dtype=np.uint64)
+    z = None
+    if zeros is not None:
+        z = np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.uint8) for x in zeros]), dtype=np.uint8)
+    out = np.zeros((k, 3, Lb), dtype=np.uint64)
+    oz = np.zeros(k, dtype=np.uint8)
+    _check(lib().plk_affine_multisummation(curve, _p64(pts), _p8(z), _p64(offsets), k, _p64(out), _p8(oz)))
+    return out, oz
+
+
+def affine_summation_best(curve: int, summation, zero=None):
+    """affine_summation_best (src/curve/curve_summations.rs:18-22)."""
+    out, oz = affine_multisummation_best(curve, [summation], None if zero is None else [zero])
+    return out[0], bool(oz[0])
+
+
+def curve_mul(curve: int, points_xyz, scalars, zero=None):
+    """CurveScalar * ProjectivePoint, elementwise over n pairs (src/curve/curve_multiplication.rs:63-70)."""
+    Lb = FIELD_LIMBS[CURVE_BASE_FIELD[curve]]
+    g = _u64(points_xyz).reshape(-1, 3, Lb)
+    s = _u64(scalars).reshape(-1, 4)
+    if g.shape[0] != s.shape[0]:
+        raise PlonkyPanic("points / scalars length mismatch")
+    z = _zero_flags(zero, g.shape[0])
+    out = np.zeros_like(g)
+    oz = np.zeros(g.shape[0], dtype=np.uint8)
+    _check(lib().plk_curve_mul(curve, _p64(g), _p8(z), _p64(s), g.shape[0], _p64(out), _p8(oz)))
     return out, oz
 
 

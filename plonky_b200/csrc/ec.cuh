@@ -129,8 +129,10 @@ struct XYZZ {
   // [k] p for a small scalar k (double-and-add, MSB first)
   PLK_HD_NOINLINE static XYZZ mul_u64(const XYZZ& p, uint64_t k) {
     XYZZ acc = identity();
-    for (int i = 63; i >= 0; --i) {
-      acc = dbl(acc);
+    int top = 63;
+    while (top >= 0 && !((k >> top) & 1)) --top;      // skip the leading zero bits
+    for (int i = top; i >= 0; --i) {
+      if (i != top) acc = dbl(acc);
       if ((k >> i) & 1) acc = add(acc, p);
     }
     return acc;

@@ -228,6 +228,51 @@ int plk_points_generate(int curve, uint64_t seed, size_t n, uint64_t* points_xy)
     PLK_CUDA(cudaStreamSynchronize(st));
   });
 }
+int plk_affine_multisummation(int curve, const uint64_t* points_xy, const uint8_t* zero, const uint64_t* offsets, size_t lists,
+                               uint64_t* out_xyz, uint8_t* out_zero) {
+  return guarded([&] {
+    if (curve_scalar_bits(curve) < 0) fail(PLK_EINVAL, "unknown curve id");
+    if (lists == 0) return;
+    if (!offsets || !out_xyz || !out_zero) fail(PLK_EINVAL, "NULL buffer");
+    for (size_t i = 0; i < lists; ++i) if (offsets[i] > offsets[i + 1]) fail(PLK_EINVAL, "offsets must be non-decreasing");
+    const size_t n = offsets[lists];
+    if (n && !points_xy) fail(PLK_EINVAL, "NULL points");
+    cudaStream_t st = thread_stream();
+    const size_t L = curve_base_limbs64(curve);
+    DevBuf d_pts(n * 2 * L * 8), d_z(n), d_off((lists + 1) * 8), d_out(lists * 3 * L * 8), d_oz(lists);
+    if (n) PLK_CUDA(cudaMemcpyAsync(d_pts.p, points_xy, n * 2 * L * 8, cudaMemcpyHostToDevice, st));
+    if (n && zero) PLK_CUDA(cudaMemcpyAsync(d_z.p, zero, n, cudaMemcpyHostToDevice, st));
+    PLK_CUDA(cudaMemcpyAsync(d_off.p, offsets, (lists + 1) * 8, cudaMemcpyHostToDevice, st));
+    ops_for(curve)->multisum(d_pts.p, zero ? d_z.as<unsigned char>() : nullptr, d_off.as<unsigned long long>(), lists, d_out.p,
+                             d_oz.as<unsigned char>(), st);
+    PLK_CUDA(cudaMemcpyAsync(out_xyz, d_out.p, lists * 3 * L * 8, cudaMemcpyDeviceToHost, st));
+    PLK_CUDA(cudaMemcpyAsync(out_zero, d_oz.p, lists, cudaMemcpyDeviceToHost, st));
+    PLK_CUDA(cudaStreamSynchronize(st));
+  });
+}
+int plk_affine_summation(int curve, const uint64_t* points_xy, const uint8_t* zero, size_t n, uint64_t* out_xyz, uint8_t* out_zero) {
+  const uint64_t offsets[2] = {0, n};
+  return plk_affine_multisummation(curve, points_xy, zero, offsets, 1, out_xyz, out_zero);
+}
+int plk_curve_mul(int curve, const uint64_t* points_xyz, const uint8_t* zero, const uint64_t* scalars, size_t n, uint64_t* out_xyz,
+                  uint8_t* out_zero) {
+  return guarded([&] {
+    if (curve_scalar_bits(curve) < 0) fail(PLK_EINVAL, "unknown curve id");
+    if (n == 0) return;
+    if (!points_xyz || !scalars || !out_xyz || !out_zero) fail(PLK_EINVAL, "NULL buffer");
+    cudaStream_t st = thread_stream();
+    const size_t L = curve_base_limbs64(curve);
+    DevBuf d_raw(n * 3 * L * 8), d_z(n), d_aff(n * 2 * L * 8), d_s(n * 32), d_out(n * 3 * L * 8), d_oz(n);
+    PLK_CUDA(cudaMemcpyAsync(d_raw.p, points_xyz, n * 3 * L * 8, cudaMemcpyHostToDevice, st));
+    if (zero) PLK_CUDA(cudaMemcpyAsync(d_z.p, zero, n, cudaMemcpyHostToDevice, st));
+    PLK_CUDA(cudaMemcpyAsync(d_s.p, scalars, n * 32, cudaMemcpyHostToDevice, st));
+    ops_for(curve)->import_points(d_raw.p, zero ? d_z.as<unsigned char>() : nullptr, n, 1, d_aff.p, st);
+    ops_for(curve)->curve_mul(d_aff.p, d_s.p, n, d_out.p, d_oz.as<unsigned char>(), st);
+    PLK_CUDA(cudaMemcpyAsync(out_xyz, d_out.p, n * 3 * L * 8, cudaMemcpyDeviceToHost, st));
+    PLK_CUDA(cudaMemcpyAsync(out_zero, d_oz.p, n, cudaMemcpyDeviceToHost, st));
+    PLK_CUDA(cudaStreamSynchronize(st));
+  });
+}
 int plk_batch_to_affine(int curve, const uint64_t* points_xyz, const uint8_t* zero, size_t n, uint64_t* out_xy, uint8_t* out_zero) {
   return guarded([&] {
     if (curve_scalar_bits(curve) < 0) fail(PLK_EINVAL, "unknown curve id");

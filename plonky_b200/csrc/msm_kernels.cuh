@@ -327,6 +327,70 @@ __global__ void batch_to_affine_kernel(const void* __restrict__ in, const unsign
 }
 
 
+// ---- affine (multi-)summation, src/curve/curve_summations.rs:18-158 --------------------------------
+// One CTA per list: every thread folds a strided slice of the list into an XYZZ accumulator with mixed
+// additions, then a shared-memory tree adds the per-thread sums; the result is normalised like every
+// other point this library returns.  (The reference batches affine additions with Montgomery's trick
+// because a CPU inversion is cheap relative to 11 multiplications; on the device the mixed XYZZ add at
+// 8M + 2S needs no inversion at all.)
+template <class C>
+__global__ void affine_multisum_kernel(const void* __restrict__ points, const unsigned char* __restrict__ zero,
+                                       const unsigned long long* __restrict__ offsets, uint32_t* __restrict__ out_xyz,
+                                       unsigned char* __restrict__ out_zero) {
+  typedef Fp<typename C::Base> F;
+  extern __shared__ uint4 sm[];
+  const unsigned long long lo = offsets[blockIdx.x], hi = offsets[blockIdx.x + 1];
+  XYZZ<C> acc = XYZZ<C>::identity();
+  for (unsigned long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    if (zero && zero[i]) continue;
+    acc = XYZZ<C>::madd(acc, load_affine<C>(points, i));
+  }
+  store_xyzz<C>(sm, threadIdx.x, acc);
+  __syncthreads();
+  for (unsigned d = blockDim.x >> 1; d > 0; d >>= 1) {
+    if (threadIdx.x < d) {
+      XYZZ<C> a = load_xyzz<C>(sm, threadIdx.x), b = load_xyzz<C>(sm, threadIdx.x + d);
+      store_xyzz<C>(sm, threadIdx.x, XYZZ<C>::add(a, b));
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    XYZZ<C> total = load_xyzz<C>(sm, 0);
+    Affine<C> a = XYZZ<C>::to_affine(total);
+    const bool z = total.is_identity();
+    F one = z ? F::zero() : F::one();
+    uint32_t* o = out_xyz + (size_t)blockIdx.x * 3 * F::N;
+    for (int i = 0; i < F::N; ++i) { o[i] = a.x.l[i]; o[F::N + i] = a.y.l[i]; o[2 * F::N + i] = one.l[i]; }
+    out_zero[blockIdx.x] = z ? 1 : 0;
+  }
+}
+
+// ---- n independent scalar multiplications, src/curve/curve_multiplication.rs:20-70 ------------------
+// (CurveScalar * ProjectivePoint: blinding terms of src/poly_commit.rs:44 and the naive oracle of the
+// reference's tests.)  One thread per pair, 4-bit fixed windows over the canonical scalar.
+template <class C>
+__global__ void __launch_bounds__(64) curve_mul_kernel(const void* __restrict__ points_xy, const void* __restrict__ scalars,
+                                                       unsigned long long n, uint32_t* __restrict__ out_xyz,
+                                                       unsigned char* __restrict__ out_zero) {
+  typedef Fp<typename C::Base> F;
+  typedef Fp<typename C::Scalar> SF;
+  const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Affine<C> p = load_affine<C>(points_xy, i);
+  const SF s = SF::to_canonical(load_fp<SF>(scalars, i));
+  XYZZ<C> acc = XYZZ<C>::identity();
+  for (int bit = SF::N * 32 - 1; bit >= 0; --bit) {
+    acc = XYZZ<C>::dbl(acc);
+    if ((s.l[bit >> 5] >> (bit & 31)) & 1) acc = XYZZ<C>::madd(acc, p);
+  }
+  Affine<C> a = XYZZ<C>::to_affine(acc);
+  const bool z = acc.is_identity();
+  F one = z ? F::zero() : F::one();
+  uint32_t* o = out_xyz + (size_t)i * 3 * F::N;
+  for (int k = 0; k < F::N; ++k) { o[k] = a.x.l[k]; o[F::N + k] = a.y.l[k]; o[2 * F::N + k] = one.l[k]; }
+  out_zero[i] = z ? 1 : 0;
+}
+
 // ---- host-side launch templates ----
 
 template <class C>
@@ -425,9 +489,26 @@ void to_affine_batch(const void* d_in, const unsigned char* d_zero, size_t n, vo
 
 
 template <class C>
+void multisum(const void* d_points, const unsigned char* d_zero, const unsigned long long* d_offsets, size_t lists, void* d_out_xyz,
+              unsigned char* d_out_zero, cudaStream_t st) {
+  typedef Fp<typename C::Base> F;
+  if (lists == 0) return;
+  const unsigned threads = 128;
+  affine_multisum_kernel<C><<<(unsigned)lists, threads, threads * 4 * sizeof(F), st>>>(d_points, d_zero, d_offsets,
+                                                                                   reinterpret_cast<uint32_t*>(d_out_xyz), d_out_zero);
+  PLK_LAUNCHED();
+}
+template <class C>
+void curve_mul(const void* d_points_xy, const void* d_scalars, size_t n, void* d_out_xyz, unsigned char* d_out_zero, cudaStream_t st) {
+  if (n == 0) return;
+  curve_mul_kernel<C><<<(unsigned)((n + 63) / 64), 64, 0, st>>>(d_points_xy, d_scalars, n, reinterpret_cast<uint32_t*>(d_out_xyz), d_out_zero);
+  PLK_LAUNCHED();
+}
+
+template <class C>
 const MsmOps* make_msm_ops() {
   static const MsmOps ops = {&table_build<C>, &import_points<C>, &execute_one<C>, &combine_partials<C>, &generate_points<C>,
-                             &to_affine_batch<C>};
+                             &to_affine_batch<C>, &multisum<C>, &curve_mul<C>};
   return &ops;
 }
 }  // namespace plk

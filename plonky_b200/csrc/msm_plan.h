@@ -41,5 +41,8 @@ struct MsmOps {
   void (*combine_partials)(const void* d_partials, size_t count, void* d_out_xyz, void* d_out_zero, cudaStream_t st);
   void (*generate_points)(uint64_t seed, size_t n, void* d_out, cudaStream_t st);
   void (*to_affine_batch)(const void* d_in, const unsigned char* d_zero, size_t n, void* d_out, unsigned char* d_out_zero, cudaStream_t st);
+  void (*multisum)(const void* d_points, const unsigned char* d_zero, const unsigned long long* d_offsets, size_t lists, void* d_out_xyz,
+                   unsigned char* d_out_zero, cudaStream_t st);
+  void (*curve_mul)(const void* d_points_xy, const void* d_scalars, size_t n, void* d_out_xyz, unsigned char* d_out_zero, cudaStream_t st);
 };
 }  // namespace plk

@@ -197,4 +197,44 @@ int plk_fft_dev(const plk_fft_plan* p, const void* d_in, size_t n_in, size_t k, 
   });
 }
 
+/* ---- domain-split transform over `world` ranks ---------------------------------
+ * N = R1 * M.  Rank r holds the rows j_1 in [row_base, row_base + rows) of the matrix x[j_1 + R1 j'] (rows
+ * of length M).  Phase A: size-M transforms of the local rows, times w_N^(j_1 k'), written in the
+ * all-to-all send layout [dest][row][k' mod (M / world)].  After the exchange rank s holds
+ * Z[j_1][kl] for all j_1 and its M / world columns; phase B transforms over j_1 in place and leaves
+ * X[k' + M k_1] at [k_1][kl], k' = s M / world + kl. */
+int plk_fft_dist_phase_a(const plk_fft_plan* plan_m, const plk_fft_plan* plan_n, const void* d_in, size_t rows, size_t row_base,
+                         unsigned world, unsigned flags, void* d_work, void* d_send, void* stream) {
+  return guarded([&] {
+    check_plan(plan_m);
+    check_plan(plan_n);
+    if (!d_in || !d_work || !d_send || rows == 0 || world == 0) fail(PLK_EINVAL, "bad arguments");
+    if (plan_m->field != plan_n->field || plan_m->log_n > plan_n->log_n) fail(PLK_EINVAL, "plans do not match");
+    if (!is_pow2(world) || world > plan_m->n) fail(PLK_EINVAL, "world must be a power of two <= M");
+    if (rows > 65535) fail(PLK_EINVAL, "too many local rows");
+    const bool inverse = (flags & PLK_FFT_INVERSE) != 0;
+    FusedOps ops;
+    ops.post_lo = plan_n->tw_lo[inverse ? 1 : 0].p;
+    ops.post_hi = plan_n->tw_hi[inverse ? 1 : 0].p;
+    ops.post_lo_bits = plan_n->lo_bits;
+    ops.post_rowmul = 1;
+    ops.post_row_base = row_base;
+    ops.final_out = d_send;
+    ops.remap = 1;
+    ops.remap_cl_log = plan_m->log_n - log2_floor(world);
+    ops.remap_rows = rows;
+    ops_for(plan_m->field)->run(plan_m, d_in, plan_m->n, plan_m->n, d_work, rows, inverse, &ops, reinterpret_cast<cudaStream_t>(stream));
+  });
+}
+int plk_fft_dist_phase_b(const plk_fft_plan* plan_n, void* d_recv, unsigned log_r1, unsigned log_cols, unsigned flags, void* stream) {
+  return guarded([&] {
+    check_plan(plan_n);
+    if (!d_recv || log_r1 > 8) fail(PLK_EINVAL, "bad arguments");
+    const bool inverse = (flags & PLK_FFT_INVERSE) != 0;
+    // phase A already divided by M (inverse); the remaining factor is R1^-1
+    const void* scale = inverse ? (const char*)plan_n->pow2_inv.p + (size_t)log_r1 * plan_n->elem_bytes : nullptr;
+    ops_for(plan_n->field)->final_pass(plan_n, d_recv, (int)log_r1, (int)log_cols, inverse, scale, reinterpret_cast<cudaStream_t>(stream));
+  });
+}
+
 }  // extern "C"

@@ -1,5 +1,6 @@
 // Host-side templates of the NTT: plan construction and pass scheduling for one field.
 #pragma once
+#include <stdlib.h>
 #include "ntt_kernels.cuh"
 
 // defined in api.cu: out[i] = in[i]^-1 elementwise on device
@@ -39,6 +40,8 @@ void plan_build(plk_fft_plan* pl) {
   // n^-1
   pl->n_inv.alloc(sizeof(F));
   PLK_CUDA(cudaMemcpyAsync(pl->n_inv.p, Tb::pow2_inv(L), sizeof(F), cudaMemcpyHostToDevice, st));
+  pl->pow2_inv.alloc((size_t)(P::TWO_ADICITY + 1) * sizeof(F));     // 2^-k for every k (contiguous host table)
+  PLK_CUDA(cudaMemcpyAsync(pl->pow2_inv.p, Tb::pow2_inv(0), (size_t)(P::TWO_ADICITY + 1) * sizeof(F), cudaMemcpyHostToDevice, st));
   for (int inv = 0; inv < 2; ++inv) {
     const uint32_t* w256 = inv ? Tb::root_inv(kSubLog <= P::TWO_ADICITY ? kSubLog : P::TWO_ADICITY)
                                : Tb::root(kSubLog <= P::TWO_ADICITY ? kSubLog : P::TWO_ADICITY);
@@ -63,7 +66,11 @@ void run_ntt(const plk_fft_plan* pl, const void* d_in, size_t n_in, size_t in_st
   static bool attr_set[8] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
-  const size_t max_smem = (size_t)(F::N / 4) * 16 * ((size_t)1 << (kSubLog + kTileColsLog));
+  const size_t wsub_bytes = sizeof(F) << (kSubLog - 1);
+  const size_t max_smem = (size_t)(F::N / 4) * 16 * ((size_t)1 << (kSubLog + kTileColsLog)) + wsub_bytes;
+  // measurement knobs (defaults are the tuned values): PLK_NTT_TILE_LOG = log2 columns per tile, PLK_NTT_THREADS
+  static const int tile_log = getenv("PLK_NTT_TILE_LOG") ? atoi(getenv("PLK_NTT_TILE_LOG")) : kTileColsLog;
+  static const int nthreads = getenv("PLK_NTT_THREADS") ? atoi(getenv("PLK_NTT_THREADS")) : kNttThreads;
   if (!attr_set[dev & 7]) {
     PLK_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
     attr_set[dev & 7] = true;
@@ -89,7 +96,7 @@ void run_ntt(const plk_fft_plan* pl, const void* d_in, size_t n_in, size_t in_st
     p.tw_hi = pl->tw_hi[inv].p;
     p.lo_bits = pl->lo_bits;
     if (p.first) {
-      p.log_t = (L - p.r) < kTileColsLog ? (L - p.r) : kTileColsLog;
+      p.log_t = (L - p.r) < tile_log ? (L - p.r) : tile_log;
       p.ndig = m - 1;
       for (int i = 0; i < m - 1; ++i) p.digs[i] = pl->dig[i];
       p.pre_lo = ops.pre_lo;
@@ -97,7 +104,7 @@ void run_ntt(const plk_fft_plan* pl, const void* d_in, size_t n_in, size_t in_st
       if (inverse && m == 1) p.scale = pl->n_inv.p;
     } else {
       p.log_m = log_m_acc;
-      p.log_t = p.log_m < kTileColsLog ? p.log_m : kTileColsLog;
+      p.log_t = p.log_m < tile_log ? p.log_m : tile_log;
       if (inverse && p.last) { p.tw_all = 1; p.tw_hi = pl->tw_hi_inv_scaled.p; }
     }
     if (p.last) {
@@ -105,12 +112,20 @@ void run_ntt(const plk_fft_plan* pl, const void* d_in, size_t n_in, size_t in_st
       p.post_hi = ops.post_hi;
       p.post_periodic = ops.post_periodic;
       p.post_mask = ops.post_mask;
+      p.post_rowmul = ops.post_rowmul;
+      p.post_row_base = ops.post_row_base;
+      p.remap = ops.remap;
+      p.remap_cl_log = ops.remap_cl_log;
+      p.remap_rows = ops.remap_rows;
+      if (ops.final_out) p.out = ops.final_out;
     }
+    // the post tables may belong to the (larger) plan of a distributed transform: their own lo_bits
+    p.post_lo_bits = (p.last && ops.post_lo_bits >= 0) ? ops.post_lo_bits : p.lo_bits;
     const size_t tiles = pl->n >> (p.r + p.log_t);
-    const size_t smem = (size_t)(F::N / 4) * 16 * ((size_t)1 << (p.r + p.log_t));
+    const size_t smem = (size_t)(F::N / 4) * 16 * ((size_t)1 << (p.r + p.log_t)) + wsub_bytes;
     if (tiles > 0x7fffffffull || k > 65535) fail(PLK_EINVAL, "transform grid too large");
     dim3 grid((unsigned)tiles, (unsigned)k);
-    ntt_pass_kernel<F><<<grid, kNttThreads, smem, st>>>(p);
+    ntt_pass_kernel<F><<<grid, nthreads, smem, st>>>(p);
     PLK_LAUNCHED();
     timer.mark(st);
     log_m_acc += p.r;
@@ -197,8 +212,36 @@ template <class P> void do_zh_table(plk_fft_plan* pl, size_t n_gates, FusedOps* 
 
 
 template <class P>
+void do_final_pass(const plk_fft_plan* pl, void* d_buf, int r, int log_cols, bool inverse, const void* d_scale, cudaStream_t st) {
+  typedef Fp<P> F;
+  NttPassParams p;
+  memset(&p, 0, sizeof(p));
+  p.log_n = r + log_cols;
+  p.r = r;
+  p.first = 0;
+  p.last = 1;
+  p.tw_none = 1;
+  p.in = d_buf;
+  p.out = d_buf;
+  p.in_stride = p.out_stride = (unsigned long long)1 << (r + log_cols);
+  p.log_m = log_cols;
+  p.log_t = log_cols < kTileColsLog ? log_cols : kTileColsLog;
+  p.wsub = pl->wsub[inverse ? 1 : 0].p;
+  p.lo_bits = pl->lo_bits;
+  p.post_lo_bits = pl->lo_bits;
+  p.scale = d_scale;
+  const size_t wsub_bytes = sizeof(F) << (kSubLog - 1);
+  const size_t smem = (size_t)(F::N / 4) * 16 * ((size_t)1 << (p.r + p.log_t)) + wsub_bytes;
+  PLK_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)((size_t)(F::N / 4) * 16 * ((size_t)1 << (kSubLog + kTileColsLog)) + wsub_bytes)));
+  const size_t tiles = ((size_t)1 << (r + log_cols)) >> (p.r + p.log_t);
+  ntt_pass_kernel<F><<<dim3((unsigned)tiles, 1), kNttThreads, smem, st>>>(p);
+  PLK_LAUNCHED();
+}
+
+template <class P>
 const NttOps* make_ntt_ops() {
-  static const NttOps ops = {&plan_build<P>, &do_run<P>, &do_coset<P>, &do_zh_table<P>};
+  static const NttOps ops = {&plan_build<P>, &do_run<P>, &do_coset<P>, &do_zh_table<P>, &do_final_pass<P>};
   return &ops;
 }
 }  // namespace plk

@@ -58,7 +58,23 @@ struct NttPassParams {
   const void* post_periodic;      // optional output multiplier tbl[k & post_mask]
   unsigned long long post_mask;
   const void* scale;              // optional constant multiplier (single-pass inverse)
+  int post_lo_bits;               // lo_bits of the post tables
+  int tw_none;                    // in-place pass without inter-pass twiddles (phase B of the distributed transform)
+  int post_rowmul;                // post factor exponent = (post_row_base + batch row) * k instead of k
+  unsigned long long post_row_base;
+  int remap;                      // final store goes to the all-to-all send layout [dest][row][k mod 2^remap_cl_log]
+  int remap_cl_log;
+  unsigned long long remap_rows;
 };
+
+// Output position of final value k of batch row `row`: natural (k) or packed for the all-to-all of the
+// domain-split transform: destination rank (k >> cl) major, then row, then the column inside the block.
+__device__ __forceinline__ unsigned long long ntt_out_index(const NttPassParams& p, unsigned long long k, unsigned row,
+                                                           unsigned long long out_stride) {
+  if (!p.remap) return (unsigned long long)row * out_stride + k;
+  const unsigned long long dest = k >> p.remap_cl_log, kl = k & ((1ull << p.remap_cl_log) - 1);
+  return ((dest * p.remap_rows + row) << p.remap_cl_log) + kl;
+}
 
 __device__ __forceinline__ unsigned bitrev(unsigned x, int bits) { return bits == 0 ? 0u : (__brev(x) >> (32 - bits)); }
 
@@ -94,7 +110,7 @@ __device__ __forceinline__ F two_level_always(const void* lo, const void* hi, in
 // Q layers of decimation-in-time butterflies on 2^Q register-resident elements whose rows are
 // base + (e << l0); `low` = base mod 2^l0 selects the twiddles.  LAYER0: l0 == 0 (twiddle 1 skipped).
 template <class F, int Q, bool LAYER0>
-__device__ __forceinline__ void dit_layers(F (&x)[1 << Q], int l0, int low, const void* wsub) {
+__device__ __forceinline__ void dit_layers(F (&x)[1 << Q], int l0, int low, const uint4* wsub) {
 #pragma unroll
   for (int t = 1; t <= Q; ++t) {
     const int half = 1 << (t - 1);
@@ -102,7 +118,7 @@ __device__ __forceinline__ void dit_layers(F (&x)[1 << Q], int l0, int low, cons
     for (int kk = 0; kk < half; ++kk) {
       const bool trivial = LAYER0 && kk == 0;
       F w;
-      if (!trivial) w = load_fp<F>(wsub, (size_t)((low + (kk << l0)) << (kSubLog - (l0 + t))));
+      if (!trivial) w = load_fp<F>(wsub, (size_t)((low + (kk << l0)) << (kSubLog - (l0 + t))));   // shared-memory copy
 #pragma unroll
       for (int blk = 0; blk < (1 << Q); blk += 2 * half) {
         F v = trivial ? x[blk + kk + half] : F::mul(x[blk + kk + half], w);
@@ -122,7 +138,7 @@ struct TileGeom {
 };
 
 template <class F, int Q, bool LAYER0>
-__device__ __forceinline__ void ntt_round(const NttPassParams& p, uint4* smem, int l0) {
+__device__ __forceinline__ void ntt_round(const NttPassParams& p, uint4* smem, const uint4* wsub, int l0) {
   const int T = 1 << p.log_t, elems = 1 << (p.r + p.log_t);
   const int groups = elems >> Q;
   for (int gi = threadIdx.x; gi < groups; gi += blockDim.x) {
@@ -136,7 +152,7 @@ __device__ __forceinline__ void ntt_round(const NttPassParams& p, uint4* smem, i
       const int row = base_row + (e << l0);
       x[e] = lds_fp<F>(smem, elems, row * T + (col ^ (row & (T - 1))));
     }
-    dit_layers<F, Q, LAYER0>(x, l0, low, p.wsub);
+    dit_layers<F, Q, LAYER0>(x, l0, low, wsub);
 #pragma unroll
     for (int e = 0; e < (1 << Q); ++e) {
       const int row = base_row + (e << l0);
@@ -153,6 +169,7 @@ __device__ __forceinline__ void ntt_round(const NttPassParams& p, uint4* smem, i
 template <class F>
 __device__ __noinline__ void ntt_pre_factors(const NttPassParams& p, const TileGeom& g, uint4* smem) {
   const int T = 1 << p.log_t, elems = 1 << (p.r + p.log_t);
+#pragma unroll 2
   for (int idx = threadIdx.x; idx < elems; idx += blockDim.x) {
     const int col = idx & (T - 1);
     const int srow = idx >> p.log_t;
@@ -166,7 +183,8 @@ __device__ __noinline__ void ntt_pre_factors(const NttPassParams& p, const TileG
     } else {
       const unsigned long long kk = g.k0 + col;
       const unsigned long long ex = ((unsigned long long)orow * kk) << (p.log_n - p.r - p.log_m);
-      if (p.tw_all) { fac = two_level_always<F>(p.tw_lo, p.tw_hi, p.lo_bits, ex); have = true; }
+      if (p.tw_none) { }
+      else if (p.tw_all) { fac = two_level_always<F>(p.tw_lo, p.tw_hi, p.lo_bits, ex); have = true; }
       else if (ex != 0) { fac = two_level<F>(p.tw_lo, p.tw_hi, p.lo_bits, ex); have = true; }
     }
     if (p.scale) {
@@ -188,7 +206,8 @@ __device__ __noinline__ void ntt_post_factors(const NttPassParams& p, const Tile
     const int sidx = (int)row * T + (col ^ ((int)row & (T - 1)));
     const unsigned long long k = p.first ? row : (g.k0 + col + (row << p.log_m));
     F x = lds_fp<F>(smem, elems, sidx);
-    if (p.post_lo && k != 0) x = F::mul(x, two_level<F>(p.post_lo, p.post_hi, p.lo_bits, k));
+    const unsigned long long pe = p.post_rowmul ? (p.post_row_base + blockIdx.y) * k : k;
+    if (p.post_lo && pe != 0) x = F::mul(x, two_level<F>(p.post_lo, p.post_hi, p.post_lo_bits, pe));
     if (p.post_periodic) x = F::mul(x, load_fp<F>(p.post_periodic, (size_t)(k & p.post_mask)));
     sts_fp<F>(smem, elems, sidx, x);
   }
@@ -202,7 +221,7 @@ __global__ void __launch_bounds__(kNttThreads, 2) ntt_pass_kernel(NttPassParams 
   const int T = 1 << p.log_t, R = 1 << p.r, elems = R * T;
   const unsigned long long tile = blockIdx.x;
   const uint4* in = reinterpret_cast<const uint4*>(p.in) + (size_t)blockIdx.y * p.in_stride * PIECES;
-  uint4* out = reinterpret_cast<uint4*>(p.out) + (size_t)blockIdx.y * p.out_stride * PIECES;
+  uint4* out = reinterpret_cast<uint4*>(p.out);   // batch row offset is applied by ntt_out_index
 
   TileGeom g;
   if (p.first) {
@@ -217,33 +236,46 @@ __global__ void __launch_bounds__(kNttThreads, 2) ntt_pass_kernel(NttPassParams 
     g.rowshift = p.log_m;
   }
 
-  // ---- load: 16-byte pieces, columns fastest (256 B contiguous per row) ----
+  // the 128 sub-transform twiddles live in shared memory behind the tile (fixed 29-cycle LDS instead of
+  // L1/L2 round trips on the butterflies' critical path)
+  uint4* wsub_s = smem + (size_t)PIECES * elems;
+  for (int idx = threadIdx.x; idx < (1 << (kSubLog - 1)) * PIECES; idx += blockDim.x)
+    wsub_s[idx] = reinterpret_cast<const uint4*>(p.wsub)[idx];
+
+  // ---- load: 16-byte pieces, columns fastest (256 B contiguous per row), global -> shared directly with
+  // cp.async (LDGSTS): all of a thread's 16 pieces are in flight at once and no register staging is
+  // needed; rows at or beyond n_in (zero padding of the LDE) are zero-filled without touching memory.
   for (int idx = threadIdx.x; idx < elems * PIECES; idx += blockDim.x) {
     const int piece = idx % PIECES;
     const int e = idx / PIECES;
     const int col = e & (T - 1);
     const int row = e >> p.log_t;
     const unsigned long long gidx = g.gbase + col + ((unsigned long long)row << g.rowshift);
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (!p.first || gidx < p.n_in) v = in[gidx * PIECES + piece];
     const int srow = (int)bitrev((unsigned)row, p.r);
-    smem[piece * elems + srow * T + (col ^ (srow & (T - 1)))] = v;
+    uint4* dst = &smem[piece * elems + srow * T + (col ^ (srow & (T - 1)))];
+    const bool present = !p.first || gidx < p.n_in;
+    const uint4* src = in + (present ? gidx * PIECES + piece : 0);
+    const unsigned nbytes = present ? 16u : 0u;
+    const unsigned saddr = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(src), "r"(nbytes) : "memory");
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
   // ---- input-side factors, then butterflies as radix-8 / 4 / 2 register rounds ----
-  if ((p.first && p.pre_lo) || !p.first || p.scale) ntt_pre_factors<F>(p, g, smem);
+  if ((p.first && p.pre_lo) || (!p.first && !p.tw_none) || p.scale) ntt_pre_factors<F>(p, g, smem);
   {
     int l0 = 0;
     const int r = p.r;
-    if (r >= 3) { ntt_round<F, 3, true>(p, smem, 0); l0 = 3; }
-    else if (r == 2) { ntt_round<F, 2, true>(p, smem, 0); l0 = 2; }
-    else if (r == 1) { ntt_round<F, 1, true>(p, smem, 0); l0 = 1; }
+    if (r >= 3) { ntt_round<F, 3, true>(p, smem, wsub_s, 0); l0 = 3; }
+    else if (r == 2) { ntt_round<F, 2, true>(p, smem, wsub_s, 0); l0 = 2; }
+    else if (r == 1) { ntt_round<F, 1, true>(p, smem, wsub_s, 0); l0 = 1; }
     while (l0 < r) {
       const int q = (r - l0 >= 3) ? 3 : (r - l0);
-      if (q == 3) ntt_round<F, 3, false>(p, smem, l0);
-      else if (q == 2) ntt_round<F, 2, false>(p, smem, l0);
-      else ntt_round<F, 1, false>(p, smem, l0);
+      if (q == 3) ntt_round<F, 3, false>(p, smem, wsub_s, l0);
+      else if (q == 2) ntt_round<F, 2, false>(p, smem, wsub_s, l0);
+      else ntt_round<F, 1, false>(p, smem, wsub_s, l0);
       l0 += q;
     }
   }
@@ -257,7 +289,9 @@ __global__ void __launch_bounds__(kNttThreads, 2) ntt_pass_kernel(NttPassParams 
       const int col = e & (T - 1);
       const int row = e >> p.log_t;
       const unsigned long long gidx = g.gbase + col + ((unsigned long long)row << g.rowshift);
-      out[gidx * PIECES + piece] = smem[piece * elems + row * T + (col ^ (row & (T - 1)))];
+      const unsigned long long oidx = p.last ? ntt_out_index(p, gidx, blockIdx.y, p.out_stride)
+                                             : (unsigned long long)blockIdx.y * p.out_stride + gidx;
+      out[oidx * PIECES + piece] = smem[piece * elems + row * T + (col ^ (row & (T - 1)))];
     }
   } else {
     // column c of the tile becomes a run of R contiguous outputs at rev_digits(jlow) * R
@@ -272,7 +306,9 @@ __global__ void __launch_bounds__(kNttThreads, 2) ntt_pass_kernel(NttPassParams 
         x >>= p.digs[i];
       }
       const unsigned long long gidx = (pos << p.r) + row;
-      out[gidx * PIECES + piece] = smem[piece * elems + row * T + (col ^ (row & (T - 1)))];
+      const unsigned long long oidx = p.last ? ntt_out_index(p, gidx, blockIdx.y, p.out_stride)
+                                             : (unsigned long long)blockIdx.y * p.out_stride + gidx;
+      out[oidx * PIECES + piece] = smem[piece * elems + row * T + (col ^ (row & (T - 1)))];
     }
   }
 }

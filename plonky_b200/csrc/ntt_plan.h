@@ -30,6 +30,7 @@ struct plk_fft_plan {
   plk::DevBuf tw_lo[2], tw_hi[2];
   plk::DevBuf tw_hi_inv_scaled;   // inverse hi table with n^-1 folded in
   plk::DevBuf n_inv;              // one element: n^-1
+  plk::DevBuf pow2_inv;           // 2^-k, k <= TWO_ADICITY
   std::mutex mu;
   std::map<std::vector<uint32_t>, CosetTables*> cosets;   // keyed by the shift's limbs
   std::map<size_t, plk::DevBuf*> zh_tables;                     // keyed by n_gates
@@ -49,6 +50,13 @@ struct FusedOps {
   const void* post_hi = nullptr;
   const void* post_periodic = nullptr;
   unsigned long long post_mask = 0;
+  // domain-split (multi-GPU) transform, phase A: twiddle w_N^(j_1 k') on the final values and packed store
+  int post_rowmul = 0;
+  unsigned long long post_row_base = 0;
+  int post_lo_bits = -1;              // lo_bits of the post tables when they belong to another (larger) plan
+  void* final_out = nullptr;          // last pass writes here (out of place) instead of d_out
+  int remap = 0, remap_cl_log = 0;
+  unsigned long long remap_rows = 0;
 };
 
 
@@ -59,5 +67,7 @@ struct NttOps {
               const FusedOps* ops, cudaStream_t st);
   void (*coset)(plk_fft_plan*, const uint64_t* shift, bool inverse, FusedOps* ops, cudaStream_t st);
   void (*zh_table)(plk_fft_plan*, size_t n_gates, FusedOps* ops, cudaStream_t st);
+  // one in-place pass of 2^r rows x 2^log_cols columns without twiddles (phase B of the domain-split transform)
+  void (*final_pass)(const plk_fft_plan*, void* d_buf, int r, int log_cols, bool inverse, const void* d_scale, cudaStream_t st);
 };
 }  // namespace plk

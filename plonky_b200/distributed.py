@@ -17,7 +17,8 @@ import torch.distributed as dist
 
 from . import lib, _check, FIELD_LIMBS, CURVE_BASE_FIELD, MsmPrecomputation
 
-__all__ = ["msm_precompute_affine_dev", "points_generate_dev", "msm_execute_dev", "msm_execute_sharded", "fft_dev"]
+__all__ = ["msm_precompute_affine_dev", "points_generate_dev", "msm_execute_dev", "msm_execute_sharded", "fft_dev",
+           "DistributedNtt"]
 
 
 def _stream_ptr() -> C.c_void_p:
@@ -68,3 +69,70 @@ def fft_dev(pre, d_in: torch.Tensor, d_out: torch.Tensor, inverse: bool = False,
     n_in = d_in.shape[-2]
     flags = (1 if inverse else 0) | (2 if coset else 0)
     _check(lib().plk_fft_dev(pre.handle, C.c_void_p(d_in.data_ptr()), n_in, k, flags, C.c_void_p(d_out.data_ptr()), _stream_ptr()))
+
+
+class DistributedNtt:
+    """Domain-split NTT of size N = 2^log_n over `world` GPUs: four-step with ONE all-to-all
+    (SURVEY.md section 8(e)).  N = R1 * M with R1 = 2^log_r1 (<= 256) the digit transformed after the exchange.
+
+      input  (rank r): rows j_1 in [r R1/G, (r+1) R1/G) of the matrix x[j_1 + R1 j'], shape (R1/G, M, L)
+      output (rank s): X[k' + M k_1] at [k_1][kl], k' = s M/G + kl, shape (R1, M/G, L)
+
+    With world == 1 the input is the R1 x M "decimated" view of x and the output is X in natural order.
+    `input_rows(x)` / `gather_natural(out)` convert between these layouts and natural order (tests, G = 1)."""
+
+    def __init__(self, field: int, log_n: int, world: int = None, rank: int = None, group=None, log_r1: int = None):
+        from . import fft_precompute, FIELD_LIMBS as FL
+        self.group = group
+        self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
+        self.rank = rank if rank is not None else (dist.get_rank(group) if dist.is_initialized() else 0)
+        g_log = self.world.bit_length() - 1
+        assert 1 << g_log == self.world, "world size must be a power of two"
+        if log_r1 is None:
+            log_r1 = min(8, log_n - g_log - 3) if log_n - g_log - 3 >= g_log else min(8, log_n // 2)
+        assert g_log <= log_r1 <= 8 and log_n - log_r1 >= g_log, "transform too small for this world size"
+        self.field, self.log_n, self.log_r1, self.log_m = field, log_n, log_r1, log_n - log_r1
+        self.L = FL[field]
+        self.rows = (1 << log_r1) // self.world
+        self.cols = (1 << self.log_m) // self.world
+        self.plan_m = fft_precompute(field, 1 << self.log_m)
+        self.plan_n = fft_precompute(field, 1 << log_n)
+        shape_in = (self.rows, 1 << self.log_m, self.L)
+        self.work = torch.empty(shape_in, dtype=torch.int64, device="cuda")
+        self.send = torch.empty(shape_in, dtype=torch.int64, device="cuda")
+        self.recv = torch.empty((1 << log_r1, self.cols, self.L), dtype=torch.int64, device="cuda")
+
+    def phase_a(self, local_rows: torch.Tensor, inverse: bool = False, rank: int = None, send: torch.Tensor = None):
+        r = self.rank if rank is None else rank
+        send = self.send if send is None else send
+        assert local_rows.shape == self.work.shape and local_rows.is_contiguous()
+        _check(lib().plk_fft_dist_phase_a(self.plan_m.handle, self.plan_n.handle, C.c_void_p(local_rows.data_ptr()), self.rows,
+                                          r * self.rows, self.world, 1 if inverse else 0, C.c_void_p(self.work.data_ptr()),
+                                          C.c_void_p(send.data_ptr()), _stream_ptr()))
+        return send
+
+    def phase_b(self, recv: torch.Tensor, inverse: bool = False):
+        _check(lib().plk_fft_dist_phase_b(self.plan_n.handle, C.c_void_p(recv.data_ptr()), self.log_r1,
+                                          self.log_m - (self.world.bit_length() - 1), 1 if inverse else 0, _stream_ptr()))
+        return recv
+
+    def forward(self, local_rows: torch.Tensor, inverse: bool = False) -> torch.Tensor:
+        """Phase A, all-to-all (NCCL), phase B.  Returns this rank's (R1, M/G, L) slice of the output."""
+        self.phase_a(local_rows, inverse)
+        if self.world == 1:
+            self.recv.copy_(self.send.view(self.recv.shape))
+        else:
+            dist.all_to_all_single(self.recv.view(-1), self.send.view(-1), group=self.group)
+        return self.phase_b(self.recv, inverse)
+
+    # ---- layout helpers (host-side, for tests and for callers that start from natural order) ----
+    def input_rows(self, x_natural: torch.Tensor, rank: int = None) -> torch.Tensor:
+        """natural-order x (N, L) -> this rank's rows: x[j_1 + R1 j'] for its j_1 block."""
+        r = self.rank if rank is None else rank
+        R1 = 1 << self.log_r1
+        m = x_natural.view(1 << self.log_m, R1, self.L).transpose(0, 1)        # [j_1][j']
+        return m[r * self.rows:(r + 1) * self.rows].contiguous()
+
+    def natural_from_outputs(self, outs) -> torch.Tensor:
+        """per-rank outputs [(R1, M/G, L)] -> natural-order X (N, L): X[k' + M k_1] = outs[s][k_1][kl]."""
+        return torch.cat(list(outs), dim=1).reshape(-1, self.L)

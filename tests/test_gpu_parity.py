@@ -306,3 +306,75 @@ def test_batch_to_affine():
     out, oz = pk.batch_to_affine(c.cid, xyz, zero)
     for i, P in enumerate(pts):
         assert array_to_point(c, out[i], oz[i]) == P
+
+
+@pytest.mark.parametrize("name", list(po.CURVES))
+def test_affine_summations(name):
+    """curve_summations.rs:164-184 cases plus longer lists, several lists at once."""
+    c = po.CURVES[name]
+    G = c.gen
+    G2 = c.double(G)
+    rng = po.SplitMix64(3 + c.cid)
+    base = po.rand_points(c, rng, 9)
+    lists = [[G, G], [G, G2], [G, G, G], [], [G, c.neg(G)], [None, G], base * 30 + [c.neg(base[0])], [G] * 257]
+    arrays, zeros, want = [], [], []
+    for pts in lists:
+        xy, z = points_to_array(c, pts)
+        arrays.append(xy)
+        zeros.append(z)
+        acc = None
+        for P in pts:
+            acc = c.add(acc, P)
+        want.append(acc)
+    out, oz = pk.affine_multisummation_best(c.cid, arrays, zeros)
+    for i in range(len(lists)):
+        assert result_point(c, out[i], oz[i]) == want[i], i
+    one, onez = pk.affine_summation_best(c.cid, arrays[6], zeros[6])
+    assert result_point(c, one, onez) == want[6]
+
+
+@pytest.mark.parametrize("name", list(po.CURVES))
+def test_curve_mul(name):
+    """test_g1_multiplication style (bls12_377_curve.rs:49-62): 10 * G == G + ... + G; random pairs vs big ints."""
+    c = po.CURVES[name]
+    q = c.scalar.p
+    rng = po.SplitMix64(8 + c.cid)
+    pts = po.rand_points(c, rng, 6) + [c.gen, c.gen, None]
+    scalars = rand_scalars(c.scalar, 15, 6) + [10, q - 1, 12345]
+    xyz, zero = proj_from_affine(c, pts)
+    out, oz = pk.curve_mul(c.cid, xyz, mont_array(c.scalar, scalars), zero)
+    for i, (s, P) in enumerate(zip(scalars, pts)):
+        assert result_point(c, out[i], oz[i]) == c.mul(s, P)
+    ten = None
+    for _ in range(10):
+        ten = c.add(ten, c.gen)
+    assert result_point(c, out[6], oz[6]) == ten
+
+
+@pytest.mark.parametrize("logn,world,inverse", [(12, 1, False), (16, 1, False), (16, 2, False), (18, 4, True), (20, 8, False), (13, 2, True)])
+def test_domain_split_ntt_emulated_ranks(logn, world, inverse):
+    """The four-step domain-split transform with the all-to-all emulated on ONE GPU: phase A per emulated rank,
+    the exchange done with tensor copies, phase B per rank -- equals the single-GPU transform bit for bit."""
+    import torch
+    from plonky_b200.distributed import DistributedNtt, fft_dev
+    f = po.TWEEDLEDEE_BASE
+    n = 1 << logn
+    x = torch.from_numpy(mont_array(f, rand_scalars(f, 600 + logn, min(n, 2048)) * (n // min(n, 2048))).view(np.int64)).cuda()
+    x = (x.cpu().numpy().view(np.uint64))                       # vary the repeated blocks a little
+    x[:, 0] ^= np.arange(n, dtype=np.uint64) & np.uint64(0xFFFF)
+    X_in = torch.from_numpy(x.view(np.int64)).cuda()
+    plan = pk.fft_precompute(f.fid, n)
+    want = torch.empty_like(X_in)
+    fft_dev(plan, X_in, want, inverse=inverse)
+    ranks = [DistributedNtt(f.fid, logn, world=world, rank=r) for r in range(world)]
+    sends = [ranks[r].phase_a(ranks[r].input_rows(X_in), inverse=inverse).clone() for r in range(world)]
+    outs = []
+    for s in range(world):
+        d = ranks[s]
+        # all-to-all: rank s receives block s of every rank's send buffer, ordered by source rank
+        blocks = [sends[r].view(world, d.rows, d.cols, d.L)[s] for r in range(world)]
+        recv = torch.cat(blocks, dim=0).contiguous()           # [j_1 global][kl]
+        outs.append(d.phase_b(recv, inverse=inverse).clone())
+    got = ranks[0].natural_from_outputs(outs)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
