@@ -227,16 +227,25 @@ def run_ours(args):
 
     hbm_peak, peak_kind = peaks()
     K, W = args.steps, max(3, args.warmup)
+    curve = {"tweedledee": 0, "tweedledum": 1, "bls12_377": 2}[args.curve]
+    curve_name = {"tweedledee": "Tweedledee", "tweedledum": "Tweedledum", "bls12_377": "BLS12-377"}[args.curve]
+    Lb = 6 if curve == 2 else 4
     n = 1 << args.msm_log_n
+    if args.total_terms:
+        n //= world
 
     # ---- setup (untimed): synthetic generators on device, fixed-base table, scalar buffers ----
-    pts = pkd.points_generate_dev(CURVE, SEED + 1 + rank * n, n)
-    table = pkd.msm_precompute_affine_dev(CURVE, pts, 11)
+    pts = pkd.points_generate_dev(curve, SEED + 1 + rank * n, n)
+    table = pkd.msm_precompute_affine_dev(curve, pts, 11)
     del pts
     NBUF = 4                                  # rotate inputs; the 1 GiB table walk alone exceeds L2 (126 MB)
-    host_scalars = [torch.from_numpy(rand_scalars_np(n, SEED + 100 * rank + i).view(np.int64)).pin_memory() for i in range(NBUF)]
+    def scalars_np(seed):
+        a = rand_scalars_np(n, seed)
+        if curve == 2:
+            a[:, 3] >>= np.uint64(2)          # 253-bit scalar field: keep the limb pattern below r
+        return a
+    host_scalars = [torch.from_numpy(scalars_np(SEED + 100 * rank + i).view(np.int64)).pin_memory() for i in range(NBUF)]
     dev_scalars = [h.cuda(non_blocking=True) for h in host_scalars]
-    Lb = 4
     out_xyz = torch.zeros((3, Lb), dtype=torch.int64, device="cuda")
     out_zero = torch.zeros(8, dtype=torch.uint8, device="cuda")
     partial = torch.zeros(4 * Lb, dtype=torch.int64, device="cuda")
@@ -275,7 +284,7 @@ def run_ours(args):
     pk.set_profiling(False)
     phases = {name: t / PK for name, t in zip(pk.MSM_PHASES, phase_acc or [])}
     acc_ms = phases.get("accumulate", float("nan"))
-    alg_bytes = n * 96                                  # 32 B scalar + 64 B affine point per term
+    alg_bytes = n * (32 + 16 * Lb)                      # 32 B scalar + one affine point per term (96 B / 128 B)
     achieved = alg_bytes / (acc_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "msm_accumulate_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": None, "peak_kind": peak_kind,
@@ -312,11 +321,11 @@ def run_ours(args):
 
     line = {
         "metric": "msm_scalar_muls_per_sec", "value": value, "unit": "scalar-muls/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u64x4 (Montgomery, 255-bit)", "data": "synthetic",
-        "config": {"workload": f"Tweedledee G1 MSM 2^{args.msm_log_n} per GPU, fixed-base table (msm_precompute once, execute timed)",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if args.total_terms else "weak", "vs_baseline": None,
+        "dtype": "u64x6 (Montgomery, 377-bit base field)" if curve == 2 else "u64x4 (Montgomery, 255-bit)", "data": "synthetic",
+        "config": {"workload": f"{curve_name} G1 MSM, {n} terms per GPU, fixed-base table (msm_precompute once, execute timed)",
                    "terms_per_gpu": n, "total_terms": world * n, "window_passed": 11,
-                   "l2": "inputs larger than L2: 1 GiB table walk per step + 4 rotating 32 MiB scalar vectors",
+                   "l2": "inputs larger than L2: the table walk per step (16 windows x terms x point size) + 4 rotating scalar vectors",
                    "multi_gpu": "shard per rank, all-gather of 128 B partials, combine on every rank" if world > 1 else "single GPU"},
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": None,
     }
@@ -324,6 +333,10 @@ def run_ours(args):
     # ---- secondary: NTT 2^24 + coset LDE (rank 0 at N = 1 only keeps the default run short) ----
     if world == 1 and not args.skip_ntt:
         line["ntt"] = bench_ntt(args, pk, pkd, torch, np, hbm_peak, peak_kind)
+    elif not args.skip_ntt:
+        res = bench_ntt_domain_split(args, pk, pkd, torch, np, dist, world, rank)
+        if rank == 0:
+            line["ntt"] = res
     if rank == 0:
         line["clocks"] = sampler.stop()
         line["clocks"]["window"] = "warm-up + timed steps + per-kernel loop + e2e (+ NTT section at N=1), 100 ms polling"
@@ -403,6 +416,34 @@ def bench_ntt(args, pk, pkd, torch, np, hbm_peak, peak_kind):
     }
 
 
+def bench_ntt_domain_split(args, pk, pkd, torch, np, dist, world, rank):
+    """One 2^24 transform split over all ranks (strong scaling): four-step, ONE all-to-all (NCCL) between the
+    phases; data resident in the distributed layouts documented in plonky_b200/distributed.py."""
+    K, W = args.steps, max(3, args.warmup)
+    n = 1 << args.ntt_log_n
+    d = pkd.DistributedNtt(NTT_FIELD, args.ntt_log_n)
+    rng = np.random.Generator(np.random.PCG64(SEED + 9 + rank))
+    rows = torch.from_numpy(rng.integers(0, 1 << 62, size=tuple(d.work.shape), dtype=np.uint64).view(np.int64)).cuda()
+    for _ in range(W):
+        d.forward(rows)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        d.forward(rows)
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / K], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    bytes_a2a = (n // world) * 32 * (world - 1) // world
+    return {"metric": "ntt_elements_per_sec", "value": n / (ms * 1e-3), "unit": "elements/s", "ms_per_step": ms, "scaling": "strong",
+            "config": {"workload": f"TweedledeeBase NTT 2^{args.ntt_log_n} domain-split over {world} GPUs (four-step, one all-to-all)",
+                       "all_to_all_bytes_sent_per_rank": bytes_a2a, "log_r1": d.log_r1}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -411,6 +452,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--msm-log-n", type=int, default=MSM_LOG_N)
     ap.add_argument("--ntt-log-n", type=int, default=NTT_LOG_N)
+    ap.add_argument("--curve", default="tweedledee", choices=["tweedledee", "tweedledum", "bls12_377"],
+                    help="MSM curve (BASELINE config 4 uses bls12_377 with --msm-log-n 22 on 8 GPUs: 2^22 terms in total)")
+    ap.add_argument("--total-terms", action="store_true", help="--msm-log-n is the TOTAL across ranks (strong scaling, config 4)")
     ap.add_argument("--skip-ntt", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()

@@ -26,7 +26,8 @@
  *
  * Threading: every call is re-entrant.  Host-buffer calls run on a per-calling-thread CUDA stream;
  *   *_dev calls run on the stream the caller passes (cudaStream_t as void*).  Handles are immutable
- *   after creation except for an internal scratch pool guarded by a mutex.
+ *   after creation except for a mutex-guarded pool of scratch buffers, one set per executing stream,
+ *   so executes issued on different streams against the same table may overlap.
  *
  * Host-pointer entry points include the host<->device copies; *_dev entry points take device
  *   pointers (cudaMalloc'ed, 16-byte aligned) and neither copy nor synchronise.
@@ -113,6 +114,11 @@ int plk_msm_parallel(int curve, const uint64_t* scalars, const uint64_t* points_
  * (padded to 8).  Asynchronous on `stream`. */
 int plk_msm_execute_dev(const plk_msm_table* t, const void* d_scalars, size_t n, void* d_out_xyz,
                         void* d_out_zero, void* stream);
+/* k scalar vectors (k*n*4 u64, row-major) against one table on device buffers: d_out_xyz k*3*L u64,
+ * d_out_zero k bytes.  The k executes are forked onto internal streams (reduction tails overlap with the
+ * next accumulation) and joined back on `stream`. */
+int plk_msm_execute_batch_dev(const plk_msm_table* t, const void* d_scalars, size_t n, size_t k,
+                              void* d_out_xyz, void* d_out_zero, void* stream);
 /* Multi-GPU: un-normalised partial sum (4*L u64, XYZZ coordinates) of this rank's shard ...      */
 int plk_msm_execute_partial_dev(const plk_msm_table* t, const void* d_scalars, size_t n,
                                 void* d_partial, void* stream);

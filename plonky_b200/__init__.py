@@ -92,6 +92,7 @@ def lib():
     L.plk_msm_execute_batch.argtypes = [vp, u64p, sz, sz, u64p, u8p]
     L.plk_msm_parallel.argtypes = [C.c_int, u64p, u64p, u8p, sz, C.c_uint, u64p, u8p]
     L.plk_msm_execute_dev.argtypes = [vp, vp, sz, vp, vp, vp]
+    L.plk_msm_execute_batch_dev.argtypes = [vp, vp, sz, sz, vp, vp, vp]
     L.plk_msm_execute_partial_dev.argtypes = [vp, vp, sz, vp, vp]
     L.plk_msm_combine_partials_dev.argtypes = [C.c_int, vp, sz, vp, vp, vp]
     L.plk_msm_partial_limbs.argtypes = [C.c_int]

@@ -283,6 +283,32 @@ struct Fp {
     }
     return prod;
   }
+
+  // a^-1 by the binary extended GCD -- the reference's own algorithm (bigint_inverse.rs:6-55 followed by the
+  // product with R^3, monty.rs:162-167).  Data-dependent control flow: used where ONE thread normalises a
+  // result (the Fermat ladder above costs ~380 dependent products there); a must be non-zero.
+  PLK_HD_NOINLINE static Fp inverse_gcd(const Fp& a) {
+    if (a.is_zero()) return a;
+    uint32_t u[N], v[N], b[N], c[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { u[i] = a.l[i]; v[i] = P::mod(i); b[i] = 0; c[i] = 0; }
+    b[0] = 1;
+    auto is_one = [](const uint32_t (&x)[N]) { uint32_t acc = x[0] ^ 1u; for (int i = 1; i < N; ++i) acc |= x[i]; return acc == 0; };
+    auto shr1 = [](uint32_t (&x)[N]) { for (int i = 0; i < N - 1; ++i) x[i] = (x[i] >> 1) | (x[i + 1] << 31); x[N - 1] >>= 1; };
+    auto add_p = [](uint32_t (&x)[N]) { uint64_t cy = 0; for (int i = 0; i < N; ++i) { cy += (uint64_t)x[i] + P::mod(i); x[i] = (uint32_t)cy; cy >>= 32; } };
+    auto less = [](const uint32_t (&x)[N], const uint32_t (&y)[N]) { for (int i = N - 1; i >= 0; --i) { if (x[i] != y[i]) return x[i] < y[i]; } return false; };
+    auto sub = [](uint32_t (&x)[N], const uint32_t (&y)[N]) { uint64_t bw = 0; for (int i = 0; i < N; ++i) { uint64_t t = (uint64_t)x[i] - y[i] - bw; x[i] = (uint32_t)t; bw = (t >> 63) & 1; } };
+    while (!is_one(u) && !is_one(v)) {
+      while (!(u[0] & 1)) { shr1(u); if (b[0] & 1) add_p(b); shr1(b); }
+      while (!(v[0] & 1)) { shr1(v); if (c[0] & 1) add_p(c); shr1(c); }
+      if (less(u, v)) { sub(v, u); if (less(c, b)) add_p(c); sub(c, b); }
+      else { sub(u, v); if (less(b, c)) add_p(b); sub(b, c); }
+    }
+    Fp r, r3;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { r.l[i] = is_one(u) ? b[i] : c[i]; r3.l[i] = P::r3(i); }
+    return mul(r, r3);
+  }
 };
 
 // 128-bit vectorised global/shared access of one element (32 B -> 2 x uint4, 48 B -> 3 x uint4)

@@ -41,20 +41,66 @@ int pick_window(size_t n) {
   return c;
 }
 
+// scratch of the stream `st` (created on first use)
+plk_msm_scratch* scratch_for(plk_msm_table* t, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(t->mu);
+  auto it = t->scratch.find(st);
+  if (it == t->scratch.end()) {
+    const MsmGeom& g = t->g;
+    const size_t entries = (size_t)g.n * g.nwin;
+    t->max_tasks = entries / kTaskSize + g.nb + 1;
+    const size_t xyzz = 2 * t->point_bytes;
+    auto* s = new plk_msm_scratch();
+    try {
+      s->counts.alloc((size_t)g.nb * 4);
+      s->offsets.alloc(((size_t)g.nb + 1) * 4);
+      s->task_off.alloc(((size_t)g.nb + 1) * 4);
+      s->cursors.alloc((size_t)g.nb * 4);
+      s->sorted.alloc((entries ? entries : 1) * 4);
+      s->partials.alloc(t->max_tasks * xyzz);
+      s->buckets.alloc((size_t)g.nb * xyzz);
+      s->ranges.alloc(((size_t)g.nb / kRangeSize + 1) * xyzz);
+    } catch (...) {
+      delete s;
+      throw;
+    }
+    it = t->scratch.emplace(st, s).first;
+  }
+  t->last = it->second;
+  return it->second;
+}
 void alloc_scratch(plk_msm_table* t) {
   const MsmGeom& g = t->g;
-  const size_t entries = (size_t)g.n * g.nwin;
-  t->max_tasks = entries / kTaskSize + g.nb + 1;
-  const size_t xyzz = 2 * t->point_bytes;
-  t->counts.alloc((size_t)g.nb * 4);
-  t->offsets.alloc(((size_t)g.nb + 1) * 4);
-  t->task_off.alloc(((size_t)g.nb + 1) * 4);
-  t->cursors.alloc((size_t)g.nb * 4);
-  t->sorted.alloc((entries ? entries : 1) * 4);
-  t->partials.alloc(t->max_tasks * xyzz);
-  t->buckets.alloc((size_t)g.nb * xyzz);
-  t->ranges.alloc(((size_t)g.nb / kRangeSize + 1) * xyzz);
-  t->result.alloc(xyzz + 3 * t->point_bytes / 2 + 16);
+  t->max_tasks = (size_t)g.n * g.nwin / kTaskSize + g.nb + 1;
+}
+void run_one(plk_msm_table* t, const void* d_scalars, void* d_out_xyz, void* d_out_zero, void* d_partial, cudaStream_t st) {
+  ops_for(t->curve)->execute_one(t, scratch_for(t, st), d_scalars, d_out_xyz, d_out_zero, d_partial, st);
+}
+// k executes on device buffers, forked round-robin onto the table's side streams and joined back on `st`: the
+// low-occupancy reduction tails of one MSM overlap with the sort / accumulation of the next ones.
+void run_batch(plk_msm_table* t, const char* d_scalars, size_t k, char* d_out_xyz, char* d_out_zero, cudaStream_t st) {
+  const size_t L = curve_base_limbs64(t->curve), sbytes = t->n * 32;
+  if (k == 1) { run_one(t, d_scalars, d_out_xyz, d_out_zero, nullptr, st); return; }
+  std::lock_guard<std::mutex> batch_lock(t->batch_mu);
+  {
+    std::lock_guard<std::mutex> lk(t->mu);
+    if (!t->fork_ev) {
+      PLK_CUDA(cudaEventCreateWithFlags(&t->fork_ev, cudaEventDisableTiming));
+      for (int i = 0; i < plk_msm_table::kSideStreams; ++i) {
+        PLK_CUDA(cudaStreamCreateWithFlags(&t->side[i], cudaStreamNonBlocking));
+        PLK_CUDA(cudaEventCreateWithFlags(&t->join_ev[i], cudaEventDisableTiming));
+      }
+    }
+  }
+  const int S = plk_msm_table::kSideStreams;
+  PLK_CUDA(cudaEventRecord(t->fork_ev, st));
+  for (int i = 0; i < S && (size_t)i < k; ++i) PLK_CUDA(cudaStreamWaitEvent(t->side[i], t->fork_ev, 0));
+  for (size_t j = 0; j < k; ++j)
+    run_one(t, d_scalars + j * sbytes, d_out_xyz + j * 3 * L * 8, d_out_zero + j, nullptr, t->side[j % S]);
+  for (int i = 0; i < S && (size_t)i < k; ++i) {
+    PLK_CUDA(cudaEventRecord(t->join_ev[i], t->side[i]));
+    PLK_CUDA(cudaStreamWaitEvent(st, t->join_ev[i], 0));
+  }
 }
 
 plk_msm_table* new_table(int curve, size_t n, unsigned w) {
@@ -105,13 +151,10 @@ void execute_host(plk_msm_table* t, const uint64_t* scalars, size_t n, size_t k,
   cudaStream_t st = thread_stream();
   const size_t L = curve_base_limbs64(t->curve);
   const size_t sbytes = n * 32;
-  std::lock_guard<std::mutex> lk(t->mu);
   char* d_s = reinterpret_cast<char*>(thread_scratch(0, sbytes * k + 16));
   char* d_o = reinterpret_cast<char*>(thread_scratch(1, k * (3 * L * 8 + 8)));
   if (n) PLK_CUDA(cudaMemcpyAsync(d_s, scalars, sbytes * k, cudaMemcpyHostToDevice, st));
-  for (size_t j = 0; j < k; ++j) {
-    ops_for(t->curve)->execute_one(t, d_s + j * sbytes, d_o + j * 3 * L * 8, d_o + k * 3 * L * 8 + j, nullptr, st);
-  }
+  run_batch(t, d_s, k, d_o, d_o + k * 3 * L * 8, st);
   PLK_CUDA(cudaMemcpyAsync(out_xyz, d_o, k * 3 * L * 8, cudaMemcpyDeviceToHost, st));
   PLK_CUDA(cudaMemcpyAsync(out_zero, d_o + k * 3 * L * 8, k, cudaMemcpyDeviceToHost, st));
   PLK_CUDA(cudaStreamSynchronize(st));
@@ -179,8 +222,7 @@ int plk_msm_execute_dev(const plk_msm_table* tc, const void* d_scalars, size_t n
     if (!t) fail(PLK_EINVAL, "NULL table");
     if (n != t->n) fail(PLK_ELENGTH, "precomputation / scalars length mismatch");
     if ((n && !d_scalars) || !d_out_xyz || !d_out_zero) fail(PLK_EINVAL, "NULL buffer");
-    std::lock_guard<std::mutex> lk(t->mu);
-    ops_for(t->curve)->execute_one(t, d_scalars, d_out_xyz, d_out_zero, nullptr, reinterpret_cast<cudaStream_t>(stream));
+    run_one(t, d_scalars, d_out_xyz, d_out_zero, nullptr, reinterpret_cast<cudaStream_t>(stream));
   });
 }
 int plk_msm_execute_partial_dev(const plk_msm_table* tc, const void* d_scalars, size_t n, void* d_partial, void* stream) {
@@ -189,8 +231,7 @@ int plk_msm_execute_partial_dev(const plk_msm_table* tc, const void* d_scalars, 
     if (!t) fail(PLK_EINVAL, "NULL table");
     if (n != t->n) fail(PLK_ELENGTH, "precomputation / scalars length mismatch");
     if ((n && !d_scalars) || !d_partial) fail(PLK_EINVAL, "NULL buffer");
-    std::lock_guard<std::mutex> lk(t->mu);
-    ops_for(t->curve)->execute_one(t, d_scalars, nullptr, nullptr, d_partial, reinterpret_cast<cudaStream_t>(stream));
+    run_one(t, d_scalars, nullptr, nullptr, d_partial, reinterpret_cast<cudaStream_t>(stream));
   });
 }
 int plk_msm_combine_partials_dev(int curve, const void* d_partials, size_t count, void* d_out_xyz, void* d_out_zero, void* stream) {
@@ -204,9 +245,22 @@ int plk_msm_last_phase_ms(const plk_msm_table* tc, float* out_ms, int cap) {
   int rc = guarded([&] {
     auto* t = const_cast<plk_msm_table*>(tc);
     if (!t || !out_ms) fail(PLK_EINVAL, "bad arguments");
-    n = t->timer.read(out_ms, cap);
+    if (!t->last) fail(PLK_EINVAL, "no execute has run against this table");
+    n = t->last->timer.read(out_ms, cap);
   });
   return rc == PLK_OK ? n : -rc;
+}
+int plk_msm_execute_batch_dev(const plk_msm_table* tc, const void* d_scalars, size_t n, size_t k, void* d_out_xyz, void* d_out_zero,
+                              void* stream) {
+  return guarded([&] {
+    auto* t = const_cast<plk_msm_table*>(tc);
+    if (!t) fail(PLK_EINVAL, "NULL table");
+    if (n != t->n) fail(PLK_ELENGTH, "precomputation / scalars length mismatch");
+    if (k == 0) return;
+    if ((n && !d_scalars) || !d_out_xyz || !d_out_zero) fail(PLK_EINVAL, "NULL buffer");
+    run_batch(t, reinterpret_cast<const char*>(d_scalars), k, reinterpret_cast<char*>(d_out_xyz), reinterpret_cast<char*>(d_out_zero),
+              reinterpret_cast<cudaStream_t>(stream));
+  });
 }
 size_t plk_msm_partial_limbs(int curve) { return 4 * (size_t)curve_base_limbs64(curve); }
 

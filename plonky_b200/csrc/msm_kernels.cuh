@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(kAccThreads) msm_accumulate_kernel(const void*
   store_xyzz<C>(partials, t, acc);
 }
 
+// The three tail kernels below run one QUAD (4 lanes) per logical work item, see QuadXYZZ in ec.cuh.
 template <class C>
 __global__ void msm_bucket_sum_kernel(const void* __restrict__ partials, const unsigned* __restrict__ task_off, unsigned nb,
                                       void* __restrict__ buckets) {
@@ -190,42 +191,62 @@ __global__ void msm_bucket_sum_kernel(const void* __restrict__ partials, const u
 //   sum_b (b - lo + 1) B_b  (running sum, curve_msm.rs:149-154)  +  lo * sum_b B_b
 template <class C>
 __global__ void msm_range_kernel(const void* __restrict__ buckets, unsigned nb, void* __restrict__ range_out) {
-  const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned r = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  const int ql = threadIdx.x & 3;
+  const unsigned qmask = 0xFu << (threadIdx.x & 28);
   const unsigned lo = r * kRangeSize;
   if (lo >= nb) return;
   unsigned hi = lo + kRangeSize;
   if (hi > nb) hi = nb;
   XYZZ<C> run = XYZZ<C>::identity(), sum = XYZZ<C>::identity();
   for (unsigned b = hi; b-- > lo;) {
-    run = XYZZ<C>::add(run, load_xyzz<C>(buckets, b));
-    sum = XYZZ<C>::add(sum, run);
+    run = QuadXYZZ<C>::add(run, load_xyzz<C>(buckets, b), ql, qmask);
+    sum = QuadXYZZ<C>::add(sum, run, ql, qmask);
   }
-  if (lo != 0 && !run.is_identity()) sum = XYZZ<C>::add(sum, XYZZ<C>::mul_u64(run, lo));
-  store_xyzz<C>(range_out, r, sum);
+  if (lo != 0 && !run.is_identity()) sum = QuadXYZZ<C>::add(sum, QuadXYZZ<C>::mul_u64(run, lo, ql, qmask), ql, qmask);
+  if (ql == 0) store_xyzz<C>(range_out, r, sum);
 }
 
-// single CTA: sum `count` XYZZ points; optionally normalise to (x, y, z = 1 | zero flag)
+// out[i] = sum of in[i * chunk .. min(count, (i + 1) * chunk)), one quad per output
+template <class C>
+__global__ void msm_sum_chunks_kernel(const void* __restrict__ in, unsigned count, unsigned chunk, void* __restrict__ out) {
+  const unsigned i = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  const int ql = threadIdx.x & 3;
+  const unsigned qmask = 0xFu << (threadIdx.x & 28);
+  const unsigned lo = i * chunk;
+  if (lo >= count) return;
+  unsigned hi = lo + chunk;
+  if (hi > count) hi = count;
+  XYZZ<C> acc = load_xyzz<C>(in, lo);
+  for (unsigned j = lo + 1; j < hi; ++j) acc = QuadXYZZ<C>::add(acc, load_xyzz<C>(in, j), ql, qmask);
+  if (ql == 0) store_xyzz<C>(out, i, acc);
+}
+
+// single CTA of (blockDim / 4) quads: sum `count` XYZZ points; optionally normalise to (x, y, z = 1 | zero flag)
 template <class C>
 __global__ void msm_final_kernel(const void* __restrict__ in, unsigned count, void* __restrict__ out_xyzz,
                                  uint32_t* __restrict__ out_xyz, unsigned char* __restrict__ out_zero) {
   typedef Fp<typename C::Base> F;
   extern __shared__ uint4 sm[];
+  const unsigned q = threadIdx.x >> 2, nq = blockDim.x >> 2;
+  const int ql = threadIdx.x & 3;
+  const unsigned qmask = 0xFu << (threadIdx.x & 28);
   XYZZ<C> acc = XYZZ<C>::identity();
-  for (unsigned i = threadIdx.x; i < count; i += blockDim.x) acc = XYZZ<C>::add(acc, load_xyzz<C>(in, i));
-  store_xyzz<C>(sm, threadIdx.x, acc);
+  for (unsigned i = q; i < count; i += nq) acc = QuadXYZZ<C>::add(acc, load_xyzz<C>(in, i), ql, qmask);
+  if (ql == 0) store_xyzz<C>(sm, q, acc);
   __syncthreads();
-  for (unsigned d = blockDim.x >> 1; d > 0; d >>= 1) {
-    if (threadIdx.x < d) {
-      XYZZ<C> a = load_xyzz<C>(sm, threadIdx.x), b = load_xyzz<C>(sm, threadIdx.x + d);
-      store_xyzz<C>(sm, threadIdx.x, XYZZ<C>::add(a, b));
-    }
+  for (unsigned d = nq >> 1; d > 0; d >>= 1) {
+    XYZZ<C> s;
+    if (q < d) s = QuadXYZZ<C>::add(load_xyzz<C>(sm, q), load_xyzz<C>(sm, q + d), ql, qmask);
+    __syncthreads();
+    if (q < d && ql == 0) store_xyzz<C>(sm, q, s);
     __syncthreads();
   }
   if (threadIdx.x == 0) {
     XYZZ<C> total = load_xyzz<C>(sm, 0);
     if (out_xyzz) store_xyzz<C>(out_xyzz, 0, total);
     if (out_xyz) {
-      Affine<C> a = XYZZ<C>::to_affine(total);
+      Affine<C> a = XYZZ<C>::to_affine_gcd(total);
       const bool z = total.is_identity();
       F one = z ? F::zero() : F::one();
       for (int i = 0; i < F::N; ++i) {
@@ -414,7 +435,8 @@ void import_points(const void* d_raw, const unsigned char* d_zero, size_t n, int
 
 // the whole pipeline for one scalar vector; writes either the normalised point or the XYZZ partial
 template <class C>
-void execute_one(plk_msm_table* t, const void* d_scalars, void* d_out_xyz, void* d_out_zero, void* d_partial, cudaStream_t st) {
+void execute_one(plk_msm_table* t, plk_msm_scratch* s, const void* d_scalars, void* d_out_xyz, void* d_out_zero, void* d_partial,
+                 cudaStream_t st) {
   typedef Fp<typename C::Base> F;
   const MsmGeom g = t->g;
   const size_t xyzz = 4 * sizeof(F);
@@ -427,44 +449,57 @@ void execute_one(plk_msm_table* t, const void* d_scalars, void* d_out_xyz, void*
     }
     return;
   }
-  PLK_CUDA(cudaMemsetAsync(t->counts.p, 0, (size_t)g.nb * 4, st));
-  t->timer.begin(st);
+  PLK_CUDA(cudaMemsetAsync(s->counts.p, 0, (size_t)g.nb * 4, st));
+  s->timer.begin(st);
   const unsigned sblocks = (unsigned)((g.n + 255) / 256);
-  msm_count_kernel<C><<<sblocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(d_scalars), g, t->counts.as<unsigned>());
+  msm_count_kernel<C><<<sblocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(d_scalars), g, s->counts.as<unsigned>());
   PLK_LAUNCHED();
-  t->timer.mark(st);
-  msm_scan_kernel<<<1, 1024, 0, st>>>(t->counts.as<unsigned>(), g.nb, t->offsets.as<unsigned>(), t->task_off.as<unsigned>(),
-                                      t->cursors.as<unsigned>());
+  s->timer.mark(st);
+  msm_scan_kernel<<<1, 1024, 0, st>>>(s->counts.as<unsigned>(), g.nb, s->offsets.as<unsigned>(), s->task_off.as<unsigned>(),
+                                      s->cursors.as<unsigned>());
   PLK_LAUNCHED();
-  t->timer.mark(st);
-  msm_scatter_kernel<C><<<sblocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(d_scalars), g, t->cursors.as<unsigned>(),
-                                                 t->sorted.as<unsigned>());
+  s->timer.mark(st);
+  msm_scatter_kernel<C><<<sblocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(d_scalars), g, s->cursors.as<unsigned>(),
+                                                 s->sorted.as<unsigned>());
   PLK_LAUNCHED();
-  t->timer.mark(st);
+  s->timer.mark(st);
   const unsigned ablocks = (unsigned)((t->max_tasks + kAccThreads - 1) / kAccThreads);
-  msm_accumulate_kernel<C><<<ablocks, kAccThreads, 0, st>>>(t->table.p, t->sorted.as<unsigned>(), t->offsets.as<unsigned>(),
-                                                            t->task_off.as<unsigned>(), g.nb, t->partials.p);
+  msm_accumulate_kernel<C><<<ablocks, kAccThreads, 0, st>>>(t->table.p, s->sorted.as<unsigned>(), s->offsets.as<unsigned>(),
+                                                            s->task_off.as<unsigned>(), g.nb, s->partials.p);
   PLK_LAUNCHED();
-  t->timer.mark(st);
-  msm_bucket_sum_kernel<C><<<(g.nb + 127) / 128, 128, 0, st>>>(t->partials.p, t->task_off.as<unsigned>(), g.nb, t->buckets.p);
+  s->timer.mark(st);
+  msm_bucket_sum_kernel<C><<<(g.nb + 127) / 128, 128, 0, st>>>(s->partials.p, s->task_off.as<unsigned>(), g.nb, s->buckets.p);
   PLK_LAUNCHED();
-  t->timer.mark(st);
+  s->timer.mark(st);
   const unsigned nranges = (g.nb + kRangeSize - 1) / kRangeSize;
-  msm_range_kernel<C><<<(nranges + 63) / 64, 64, 0, st>>>(t->buckets.p, g.nb, t->ranges.p);
+  msm_range_kernel<C><<<(4 * nranges + 63) / 64, 64, 0, st>>>(s->buckets.p, g.nb, s->ranges.p);
   PLK_LAUNCHED();
-  t->timer.mark(st);
-  const unsigned fthreads = nranges >= 256 ? 256 : (nranges >= 32 ? 32 : 1);
-  msm_final_kernel<C><<<1, fthreads, fthreads * xyzz, st>>>(t->ranges.p, nranges, d_partial, reinterpret_cast<uint32_t*>(d_out_xyz),
-                                                            reinterpret_cast<unsigned char*>(d_out_zero));
+  s->timer.mark(st);
+  // final: chunks of 8 -> <= 128 quads -> tree -> normalise (the chunk sums reuse the partials buffer)
+  const void* fin = s->ranges.p;
+  unsigned fcount = nranges;
+  while (fcount > 64) {
+    const unsigned chunk = (fcount + 63) / 64 < 8 ? (fcount + 63) / 64 : 8;
+    const unsigned nout = (fcount + chunk - 1) / chunk;
+    msm_sum_chunks_kernel<C><<<(4 * nout + 63) / 64, 64, 0, st>>>(fin, fcount, chunk, s->partials.p);
+    PLK_LAUNCHED();
+    fin = s->partials.p;
+    fcount = nout;
+  }
+  unsigned fquads = 1;
+  while (fquads < fcount && fquads < 64) fquads <<= 1;
+  msm_final_kernel<C><<<1, 4 * fquads, fquads * xyzz, st>>>(fin, fcount, d_partial, reinterpret_cast<uint32_t*>(d_out_xyz),
+                                                          reinterpret_cast<unsigned char*>(d_out_zero));
   PLK_LAUNCHED();
-  t->timer.mark(st);
+  s->timer.mark(st);
 }
 
 template <class C>
 void combine_partials(const void* d_partials, size_t count, void* d_out_xyz, void* d_out_zero, cudaStream_t st) {
   typedef Fp<typename C::Base> F;
-  const unsigned fthreads = count >= 32 ? 32 : 1;
-  msm_final_kernel<C><<<1, fthreads, fthreads * 4 * sizeof(F), st>>>(d_partials, (unsigned)count, nullptr,
+  unsigned fquads = 1;
+  while (fquads < count && fquads < 8) fquads <<= 1;
+  msm_final_kernel<C><<<1, 4 * fquads, fquads * 4 * sizeof(F), st>>>(d_partials, (unsigned)count, nullptr,
                                                                      reinterpret_cast<uint32_t*>(d_out_xyz),
                                                                      reinterpret_cast<unsigned char*>(d_out_zero));
   PLK_LAUNCHED();

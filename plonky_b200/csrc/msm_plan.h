@@ -1,5 +1,6 @@
 // Host-side structures of the MSM (shared by the per-curve kernel translation units and the C ABI).
 #pragma once
+#include <map>
 #include <mutex>
 #include "common.cuh"
 
@@ -17,6 +18,14 @@ struct MsmGeom {
 
 }  // namespace plk
 
+// Scratch of ONE in-flight execute.  A table owns a small pool of these, one per CUDA stream that has
+// executed against it, so that executes issued on different streams (the batch entry points fork onto
+// internal streams; independent host threads use their own) never share buffers.
+struct plk_msm_scratch {
+  plk::DevBuf counts, offsets, task_off, cursors, sorted, partials, buckets, ranges;
+  plk::PhaseTimer timer;   // count | scan | scatter | accumulate | bucket_sum | range | final
+};
+
 struct plk_msm_table {
   int curve = 0;
   size_t n = 0;
@@ -24,20 +33,29 @@ struct plk_msm_table {
   plk::MsmGeom g;
   size_t point_bytes = 64; // affine point
   plk::DevBuf table;            // nwin * n affine points, window-major
-  // scratch (one execute at a time per table)
-  std::mutex mu;
-  plk::DevBuf counts, offsets, task_off, cursors, sorted, partials, buckets, ranges, result;
   size_t max_tasks = 0;
-  plk::PhaseTimer timer;   // count | scan | scatter | accumulate | bucket_sum | range | final
+  std::mutex mu;                // guards the pools below (not the execution)
+  std::mutex batch_mu;          // serialises the fork/join enqueue of the batch entry points
+  std::map<cudaStream_t, plk_msm_scratch*> scratch;   // keyed by the executing stream
+  plk_msm_scratch* last = nullptr;                     // scratch of the most recent execute (phase timings)
+  static constexpr int kSideStreams = 4;
+  cudaStream_t side[kSideStreams] = {nullptr, nullptr, nullptr, nullptr};   // fork/join streams of the batch entry points
+  cudaEvent_t fork_ev = nullptr, join_ev[kSideStreams] = {nullptr, nullptr, nullptr, nullptr};
+  ~plk_msm_table() {
+    for (auto& kv : scratch) delete kv.second;
+    for (auto s : side) if (s) cudaStreamDestroy(s);
+    if (fork_ev) cudaEventDestroy(fork_ev);
+    for (auto e : join_ev) if (e) cudaEventDestroy(e);
+  }
 };
-
 
 namespace plk {
 // per-curve entry points (one translation unit per curve keeps ptxas time parallel)
 struct MsmOps {
   void (*table_build)(plk_msm_table* t, const void* d_points, cudaStream_t st);
   void (*import_points)(const void* d_raw, const unsigned char* d_zero, size_t n, int projective, void* d_out, cudaStream_t st);
-  void (*execute_one)(plk_msm_table* t, const void* d_scalars, void* d_out_xyz, void* d_out_zero, void* d_partial, cudaStream_t st);
+  void (*execute_one)(plk_msm_table* t, plk_msm_scratch* s, const void* d_scalars, void* d_out_xyz, void* d_out_zero, void* d_partial,
+                      cudaStream_t st);
   void (*combine_partials)(const void* d_partials, size_t count, void* d_out_xyz, void* d_out_zero, cudaStream_t st);
   void (*generate_points)(uint64_t seed, size_t n, void* d_out, cudaStream_t st);
   void (*to_affine_batch)(const void* d_in, const unsigned char* d_zero, size_t n, void* d_out, unsigned char* d_out_zero, cudaStream_t st);

@@ -17,7 +17,7 @@ import torch.distributed as dist
 
 from . import lib, _check, FIELD_LIMBS, CURVE_BASE_FIELD, MsmPrecomputation
 
-__all__ = ["msm_precompute_affine_dev", "points_generate_dev", "msm_execute_dev", "msm_execute_sharded", "fft_dev",
+__all__ = ["msm_precompute_affine_dev", "points_generate_dev", "msm_execute_dev", "msm_execute_sharded", "msm_execute_batch_dev", "fft_dev",
            "DistributedNtt"]
 
 
@@ -47,6 +47,14 @@ def msm_execute_dev(pre: MsmPrecomputation, scalars: torch.Tensor, out_xyz: torc
     """Asynchronous msm_execute on device buffers: scalars (n, 4) int64, out_xyz (3, L) int64, out_zero (8,) uint8."""
     _check(lib().plk_msm_execute_dev(pre.handle, C.c_void_p(scalars.data_ptr()), scalars.shape[0],
                                      C.c_void_p(out_xyz.data_ptr()), C.c_void_p(out_zero.data_ptr()), _stream_ptr()))
+
+
+def msm_execute_batch_dev(pre: MsmPrecomputation, scalars_k: torch.Tensor, out_xyz: torch.Tensor, out_zero: torch.Tensor):
+    """k executes against one table: scalars_k (k, n, 4) int64, out_xyz (k, 3, L) int64, out_zero (>= k,) uint8 --
+    the device-resident body of commit_polynomials (src/plonk_util.rs:215-231)."""
+    k, n = scalars_k.shape[0], scalars_k.shape[1]
+    _check(lib().plk_msm_execute_batch_dev(pre.handle, C.c_void_p(scalars_k.data_ptr()), n, k, C.c_void_p(out_xyz.data_ptr()),
+                                           C.c_void_p(out_zero.data_ptr()), _stream_ptr()))
 
 
 def msm_execute_sharded(pre: MsmPrecomputation, scalars: torch.Tensor, partial: torch.Tensor, gathered: torch.Tensor,

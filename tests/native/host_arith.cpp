@@ -26,6 +26,7 @@ template <class P> static int field_op(int op, const uint64_t* a, const uint64_t
       case 6: r = F::to_canonical(x); break;
       case 7: r = F::from_canonical(x); break;
       case 8: r = F::dbl(x); break;
+      case 9: r = F::inverse_gcd(x); break;
       default: return -1;
     }
     memcpy(out + i * W, r.l, 4 * F::N);

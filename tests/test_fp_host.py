@@ -60,6 +60,8 @@ def test_field_ops(lib, name):
     assert canon_list(f, fop(lib, f, 8, V)) == [2 * x % f.p for x in vals]
     nz = [x for x in vals if x][:40]
     assert canon_list(f, fop(lib, f, 5, mont_array(f, nz))) == [f.inv(x) for x in nz]
+    nz_all = [x for x in vals if x]
+    assert canon_list(f, fop(lib, f, 9, mont_array(f, nz_all))) == [f.inv(x) for x in nz_all]      # binary-GCD inverse
     raw = ints_to_limbs(vals, f.limbs)
     m = fop(lib, f, 7, raw)
     assert limbs_to_ints(m) == [f.to_mont(x) for x in vals]

@@ -279,6 +279,34 @@ def test_msm_batch_and_linearity():
     assert result_point(c, s_out, s_z) == c.add(pts[0], pts[1])
 
 
+def test_msm_batch_dev_concurrent_streams():
+    """k executes forked onto the table's internal streams (per-stream scratch) give the same points as k
+    sequential executes, and executes issued from two torch streams against one table do not interfere."""
+    import torch
+    from plonky_b200 import distributed as pkd
+    c = po.TWEEDLEDEE
+    n, k = 5000, 7
+    xy = torch.from_numpy(rp.gen_points(c.cid, 21, n).view(np.int64)).cuda()
+    pre = pkd.msm_precompute_affine_dev(c.cid, xy, 11)
+    rows = np.stack([mont_array(c.scalar, rand_scalars(c.scalar, 300 + i, n)) for i in range(k)])
+    S = torch.from_numpy(rows.view(np.int64)).cuda()
+    out = torch.zeros((k, 3, 4), dtype=torch.int64, device="cuda")
+    oz = torch.zeros(16, dtype=torch.uint8, device="cuda")
+    pkd.msm_execute_batch_dev(pre, S, out, oz)
+    torch.cuda.synchronize()
+    single = torch.zeros((k, 3, 4), dtype=torch.int64, device="cuda")
+    sz = torch.zeros((k, 8), dtype=torch.uint8, device="cuda")
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for i in range(k):
+        with torch.cuda.stream(streams[i % 2]):
+            pkd.msm_execute_dev(pre, S[i], single[i], sz[i])
+    torch.cuda.synchronize()
+    assert torch.equal(out, single)
+    for i in range(k):
+        want, wz = pk.msm_execute(pre, rows[i])
+        assert np.array_equal(out[i].cpu().numpy().view(np.uint64), want)
+
+
 def test_msm_skewed_scalars():
     """All scalars equal / tiny: every term lands in the same bucket (worst-case load balance) and
     repeated identical points force the doubling branch."""
