@@ -1,4 +1,5 @@
 // C ABI of the MSM (include/plonky_b200.h); kernels live in msm_kernels.cuh, one translation unit per curve.
+#include <stdlib.h>
 #include "msm_plan.h"
 #include "field_constants.cuh"
 
@@ -33,7 +34,11 @@ int curve_base_limbs64(int curve) { return curve == PLK_CURVE_BLS12_377 ? 6 : 4;
 
 int pick_window(size_t n) {
   // all windows share one bucket set (fixed-base table), so the bucket reduction costs ~2^c additions
-  // once and the accumulation n * ceil(256 / c): large windows win early.
+  // once and the accumulation n * ceil(256 / c): large windows win early.  PLK_MSM_WINDOW overrides (tuning).
+  if (const char* e = getenv("PLK_MSM_WINDOW")) {
+    int c = atoi(e);
+    if (c >= 2 && c <= 24) return c;
+  }
   int lg = log2_ceil(n ? n : 1);
   int c = lg - 1;
   if (c < 4) c = 4;
@@ -48,7 +53,7 @@ plk_msm_scratch* scratch_for(plk_msm_table* t, cudaStream_t st) {
   if (it == t->scratch.end()) {
     const MsmGeom& g = t->g;
     const size_t entries = (size_t)g.n * g.nwin;
-    t->max_tasks = entries / kTaskSize + g.nb + 1;
+    t->max_tasks = entries / g.task + g.nb + 1;
     const size_t xyzz = 2 * t->point_bytes;
     auto* s = new plk_msm_scratch();
     try {
@@ -60,6 +65,7 @@ plk_msm_scratch* scratch_for(plk_msm_table* t, cudaStream_t st) {
       s->partials.alloc(t->max_tasks * xyzz);
       s->buckets.alloc((size_t)g.nb * xyzz);
       s->ranges.alloc(((size_t)g.nb / kRangeSize + 1) * xyzz);
+      s->big_list.alloc(((size_t)g.nb + 1) * 4);
     } catch (...) {
       delete s;
       throw;
@@ -71,7 +77,7 @@ plk_msm_scratch* scratch_for(plk_msm_table* t, cudaStream_t st) {
 }
 void alloc_scratch(plk_msm_table* t) {
   const MsmGeom& g = t->g;
-  t->max_tasks = (size_t)g.n * g.nwin / kTaskSize + g.nb + 1;
+  t->max_tasks = (size_t)g.n * g.nwin / g.task + g.nb + 1;
 }
 void run_one(plk_msm_table* t, const void* d_scalars, void* d_out_xyz, void* d_out_zero, void* d_partial, cudaStream_t st) {
   ops_for(t->curve)->execute_one(t, scratch_for(t, st), d_scalars, d_out_xyz, d_out_zero, d_partial, st);
@@ -115,6 +121,15 @@ plk_msm_table* new_table(int curve, size_t n, unsigned w) {
   t->g.c = pick_window(n);
   t->g.nwin = (bits + 1 + t->g.c - 1) / t->g.c;
   t->g.nb = 1u << (t->g.c - 1);
+  // task size: aim at >= ~75 K accumulate threads (4 CTAs of 128 on each of the 148 SMs) so that small MSMs
+  // still fill the machine; large ones use the full 64-entry tasks
+  {
+    const unsigned long long entries = (unsigned long long)n * t->g.nwin;
+    unsigned s = kTaskSizeMax;
+    while (s > 8 && entries / s < 75000) s >>= 1;
+    if (const char* e = getenv("PLK_MSM_TASK")) { int v = atoi(e); if (v >= 1 && v <= 1024) s = (unsigned)v; }
+    t->g.task = s;
+  }
   if ((unsigned long long)n * t->g.nwin >= (1ull << 31)) { delete t; fail(PLK_EINVAL, "too many terms for 31-bit table slots"); }
   return t;
 }

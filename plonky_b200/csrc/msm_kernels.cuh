@@ -65,7 +65,7 @@ __global__ void msm_count_kernel(const uint4* __restrict__ scalars, MsmGeom g, u
 
 // single CTA: offsets[b] = exclusive sum of counts, task_off[b] = exclusive sum of ceil(count / S);
 // offsets[nb] / task_off[nb] = totals; cursors[b] = offsets[b] (scatter positions)
-static __global__ void msm_scan_kernel(const unsigned* __restrict__ counts, unsigned nb, unsigned* __restrict__ offsets,
+static __global__ void msm_scan_kernel(const unsigned* __restrict__ counts, unsigned nb, unsigned task, unsigned* __restrict__ offsets,
                                 unsigned* __restrict__ task_off, unsigned* __restrict__ cursors) {
   __shared__ unsigned s_a[1024], s_b[1024];
   __shared__ unsigned carry_a, carry_b;
@@ -74,7 +74,7 @@ static __global__ void msm_scan_kernel(const unsigned* __restrict__ counts, unsi
   for (unsigned base = 0; base < nb; base += 1024) {
     unsigned i = base + threadIdx.x;
     unsigned ca = i < nb ? counts[i] : 0;
-    unsigned cb = (ca + kTaskSize - 1) / kTaskSize;
+    unsigned cb = (ca + task - 1) / task;
     s_a[threadIdx.x] = ca;
     s_b[threadIdx.x] = cb;
     __syncthreads();
@@ -144,7 +144,7 @@ __device__ __forceinline__ XYZZ<C> load_xyzz(const void* base, size_t idx) {
 template <class C>
 __global__ void __launch_bounds__(kAccThreads) msm_accumulate_kernel(const void* __restrict__ table, const unsigned* __restrict__ sorted,
                                                                      const unsigned* __restrict__ offsets,
-                                                                     const unsigned* __restrict__ task_off, unsigned nb,
+                                                                     const unsigned* __restrict__ task_off, unsigned nb, unsigned task,
                                                                      void* __restrict__ partials) {
   typedef Fp<typename C::Base> F;
   const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -157,9 +157,9 @@ __global__ void __launch_bounds__(kAccThreads) msm_accumulate_kernel(const void*
     if (task_off[mid] <= t) lo = mid; else hi = mid;
   }
   const unsigned b = lo;
-  const unsigned start = offsets[b] + (t - task_off[b]) * kTaskSize;
+  const unsigned start = offsets[b] + (t - task_off[b]) * task;
   unsigned end = offsets[b + 1];
-  if (end > start + kTaskSize) end = start + kTaskSize;
+  if (end > start + task) end = start + task;
   XYZZ<C> acc = XYZZ<C>::identity();
   unsigned e = sorted[start];
   Affine<C> next = load_affine<C>(table, e & 0x7fffffffu);
@@ -179,12 +179,42 @@ __global__ void __launch_bounds__(kAccThreads) msm_accumulate_kernel(const void*
 // The three tail kernels below run one QUAD (4 lanes) per logical work item, see QuadXYZZ in ec.cuh.
 template <class C>
 __global__ void msm_bucket_sum_kernel(const void* __restrict__ partials, const unsigned* __restrict__ task_off, unsigned nb,
-                                      void* __restrict__ buckets) {
+                                      void* __restrict__ buckets, unsigned* __restrict__ big_list) {
   const unsigned b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
+  const unsigned t0 = task_off[b], t1 = task_off[b + 1];
+  if (t1 - t0 > kBigBucket) {            // skewed digit distribution: leave it to msm_big_bucket_kernel
+    big_list[1 + atomicAdd(&big_list[0], 1u)] = b;
+    return;
+  }
   XYZZ<C> acc = XYZZ<C>::identity();
-  for (unsigned t = task_off[b]; t < task_off[b + 1]; ++t) acc = XYZZ<C>::add(acc, load_xyzz<C>(partials, t));
+  for (unsigned t = t0; t < t1; ++t) acc = XYZZ<C>::add(acc, load_xyzz<C>(partials, t));
   store_xyzz<C>(buckets, b, acc);
+}
+// Buckets holding very many entries (all scalars equal, a short top window, ...): one CTA per bucket, strided
+// partial sums per thread + shared-memory tree, so that the worst case stays a log-depth reduction.
+template <class C>
+__global__ void __launch_bounds__(256) msm_big_bucket_kernel(const void* __restrict__ partials, const unsigned* __restrict__ task_off,
+                                                             void* __restrict__ buckets, const unsigned* __restrict__ big_list) {
+  extern __shared__ uint4 sm[];
+  const unsigned nbig = big_list[0];
+  for (unsigned i = blockIdx.x; i < nbig; i += gridDim.x) {
+    const unsigned b = big_list[1 + i];
+    const unsigned t0 = task_off[b], t1 = task_off[b + 1];
+    XYZZ<C> acc = XYZZ<C>::identity();
+    for (unsigned t = t0 + threadIdx.x; t < t1; t += blockDim.x) acc = XYZZ<C>::add(acc, load_xyzz<C>(partials, t));
+    store_xyzz<C>(sm, threadIdx.x, acc);
+    __syncthreads();
+    for (unsigned d = blockDim.x >> 1; d > 0; d >>= 1) {
+      if (threadIdx.x < d) {
+        XYZZ<C> x = load_xyzz<C>(sm, threadIdx.x), y = load_xyzz<C>(sm, threadIdx.x + d);
+        store_xyzz<C>(sm, threadIdx.x, XYZZ<C>::add(x, y));
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) store_xyzz<C>(buckets, b, load_xyzz<C>(sm, 0));
+    __syncthreads();
+  }
 }
 
 // bucket index b carries weight (b + 1).  Range [lo, lo + R): sum_b (b + 1) B_b =
@@ -450,12 +480,13 @@ void execute_one(plk_msm_table* t, plk_msm_scratch* s, const void* d_scalars, vo
     return;
   }
   PLK_CUDA(cudaMemsetAsync(s->counts.p, 0, (size_t)g.nb * 4, st));
+  PLK_CUDA(cudaMemsetAsync(s->big_list.p, 0, 4, st));
   s->timer.begin(st);
   const unsigned sblocks = (unsigned)((g.n + 255) / 256);
   msm_count_kernel<C><<<sblocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(d_scalars), g, s->counts.as<unsigned>());
   PLK_LAUNCHED();
   s->timer.mark(st);
-  msm_scan_kernel<<<1, 1024, 0, st>>>(s->counts.as<unsigned>(), g.nb, s->offsets.as<unsigned>(), s->task_off.as<unsigned>(),
+  msm_scan_kernel<<<1, 1024, 0, st>>>(s->counts.as<unsigned>(), g.nb, g.task, s->offsets.as<unsigned>(), s->task_off.as<unsigned>(),
                                       s->cursors.as<unsigned>());
   PLK_LAUNCHED();
   s->timer.mark(st);
@@ -465,10 +496,13 @@ void execute_one(plk_msm_table* t, plk_msm_scratch* s, const void* d_scalars, vo
   s->timer.mark(st);
   const unsigned ablocks = (unsigned)((t->max_tasks + kAccThreads - 1) / kAccThreads);
   msm_accumulate_kernel<C><<<ablocks, kAccThreads, 0, st>>>(t->table.p, s->sorted.as<unsigned>(), s->offsets.as<unsigned>(),
-                                                            s->task_off.as<unsigned>(), g.nb, s->partials.p);
+                                                            s->task_off.as<unsigned>(), g.nb, g.task, s->partials.p);
   PLK_LAUNCHED();
   s->timer.mark(st);
-  msm_bucket_sum_kernel<C><<<(g.nb + 127) / 128, 128, 0, st>>>(s->partials.p, s->task_off.as<unsigned>(), g.nb, s->buckets.p);
+  msm_bucket_sum_kernel<C><<<(g.nb + 127) / 128, 128, 0, st>>>(s->partials.p, s->task_off.as<unsigned>(), g.nb, s->buckets.p,
+                                                               s->big_list.as<unsigned>());
+  PLK_LAUNCHED();
+  msm_big_bucket_kernel<C><<<64, 256, 256 * xyzz, st>>>(s->partials.p, s->task_off.as<unsigned>(), s->buckets.p, s->big_list.as<unsigned>());
   PLK_LAUNCHED();
   s->timer.mark(st);
   const unsigned nranges = (g.nb + kRangeSize - 1) / kRangeSize;

@@ -5,7 +5,8 @@
 #include "common.cuh"
 
 namespace plk {
-constexpr int kTaskSize = 64;        // S: additions per accumulate task
+constexpr int kTaskSizeMax = 64;     // S: additions per accumulate task (smaller for small MSMs: more threads)
+constexpr int kBigBucket = 32;       // buckets with more task partials than this are summed by a whole CTA
 constexpr int kRangeSize = 8;        // buckets per running-sum range
 constexpr int kAccThreads = 128;
 
@@ -14,6 +15,7 @@ struct MsmGeom {
   int c;                    // window bits
   int nwin;                 // windows = ceil((BITS + 1) / c)
   unsigned nb;              // buckets = 2^(c-1)
+  unsigned task;            // S: entries per accumulate task (power of two, <= kTaskSizeMax)
 };
 
 }  // namespace plk
@@ -22,7 +24,7 @@ struct MsmGeom {
 // executed against it, so that executes issued on different streams (the batch entry points fork onto
 // internal streams; independent host threads use their own) never share buffers.
 struct plk_msm_scratch {
-  plk::DevBuf counts, offsets, task_off, cursors, sorted, partials, buckets, ranges;
+  plk::DevBuf counts, offsets, task_off, cursors, sorted, partials, buckets, ranges, big_list;   // big_list[0] = count
   plk::PhaseTimer timer;   // count | scan | scatter | accumulate | bucket_sum | range | final
 };
 
