@@ -49,6 +49,16 @@ def peaks():
         return 6650.0, "fallback"
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed `ncu --set full`
+    capture of the same workload (profiles/ncu_traffic.json, written by tools/ncu_summary.py --traffic)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -236,7 +246,10 @@ def run_ours(args):
 
     # ---- setup (untimed): synthetic generators on device, fixed-base table, scalar buffers ----
     pts = pkd.points_generate_dev(curve, SEED + 1 + rank * n, n)
-    table = pkd.msm_precompute_affine_dev(curve, pts, 11)
+    torch.cuda.synchronize()
+    t_pre = time.perf_counter()
+    table = pkd.msm_precompute_affine_dev(curve, pts, 11)        # synchronous: the msm_precompute of the reference
+    precompute_ms = (time.perf_counter() - t_pre) * 1e3
     del pts
     NBUF = 4                                  # rotate inputs; the 1 GiB table walk alone exceeds L2 (126 MB)
     def scalars_np(seed):
@@ -287,7 +300,8 @@ def run_ours(args):
     alg_bytes = n * (32 + 16 * Lb)                      # 32 B scalar + one affine point per term (96 B / 128 B)
     achieved = alg_bytes / (acc_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "msm_accumulate_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_kind": peak_kind,
+                "frac": achieved / hbm_peak, "traffic": ncu_traffic("msm_accumulate_kernel") if (curve == 0 and n == 1 << 20) else None,
+                "peak_kind": peak_kind,
                 "kernel_ms": acc_ms, "kernel_share_of_step": acc_ms / sum(phases.values()) if phases else None,
                 "phases_ms": phases,
                 "note": "integer-ALU bound (IMAD.WIDE chains), not HBM bound: see DESIGN.md; table walk reads nwin*64 B per term"}
@@ -324,7 +338,7 @@ def run_ours(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if args.total_terms else "weak", "vs_baseline": None,
         "dtype": "u64x6 (Montgomery, 377-bit base field)" if curve == 2 else "u64x4 (Montgomery, 255-bit)", "data": "synthetic",
         "config": {"workload": f"{curve_name} G1 MSM, {n} terms per GPU, fixed-base table (msm_precompute once, execute timed)",
-                   "terms_per_gpu": n, "total_terms": world * n, "window_passed": 11,
+                   "terms_per_gpu": n, "total_terms": world * n, "window_passed": 11, "precompute_ms_untimed": precompute_ms,
                    "l2": "inputs larger than L2: the table walk per step (16 windows x terms x point size) + 4 rotating scalar vectors",
                    "multi_gpu": "shard per rank, all-gather of 128 B partials, combine on every rank" if world > 1 else "single GPU"},
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": None,
@@ -409,7 +423,8 @@ def bench_ntt(args, pk, pkd, torch, np, hbm_peak, peak_kind):
         "coset_lde_elements_per_sec": n / (lde_ms * 1e-3),
         "launches_per_transform": int(launches),
         "roofline": {"bound": "hbm", "kernel": "ntt_pass_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": None, "peak_kind": peak_kind, "pass_ms": passes,
+                     "frac": achieved / hbm_peak, "traffic": ncu_traffic("ntt_pass_kernel") if args.ntt_log_n == 24 else None,
+                     "peak_kind": peak_kind, "pass_ms": passes,
                      "note": "algorithmic bytes 2*n*32 over the sum of the pass launches; the 3-pass design moves 3x that; ALU bound"},
         "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "elements/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": n * 32,
                 "ms_per_step": e2e_ms},

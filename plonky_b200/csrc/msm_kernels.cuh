@@ -290,26 +290,48 @@ __global__ void msm_final_kernel(const void* __restrict__ in, unsigned count, vo
 }
 
 // ---- table construction: [2^(c j)] P_i for j < nwin (curve_msm.rs:40-52 with our own window) ----
+// One thread per generator.  Forward sweep: c doublings per window in XYZZ; the un-normalised (X, Y) go to the
+// table slot, (ZZ, ZZZ, running product of ZZ*ZZZ) to a scratch strip.  One inversion of the total product
+// (Montgomery's trick, the batch_to_affine of the reference, curve.rs:216-232), then a backward sweep
+// normalises every power with 7 products instead of one ~380-product inversion each.
 template <class C>
 __global__ void __launch_bounds__(128) msm_table_kernel(const void* __restrict__ points, unsigned long long n, int c, int nwin,
-                                                        void* __restrict__ table) {
+                                                        void* __restrict__ table, void* __restrict__ scratch) {
   typedef Fp<typename C::Base> F;
   const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
   Affine<C> p = load_affine<C>(points, i);
-  // window 0 is the point itself
-  store_fp<F>(table, 2 * i, p.x);
+  store_fp<F>(table, 2 * i, p.x);            // window 0 is the point itself
   store_fp<F>(table, 2 * i + 1, p.y);
+  if (p.is_identity()) {                     // every power of the identity is the identity
+    for (int j = 1; j < nwin; ++j) {
+      store_fp<F>(table, 2 * ((size_t)j * n + i), p.x);
+      store_fp<F>(table, 2 * ((size_t)j * n + i) + 1, p.y);
+    }
+    return;
+  }
   XYZZ<C> q = XYZZ<C>::from_affine(p);
+  F prod = F::one();
   for (int j = 1; j < nwin; ++j) {
     for (int k = 0; k < c; ++k) q = XYZZ<C>::dbl(q);
-    // normalise this power and restart from the affine form: keeps the inversion count at one per
-    // power but needs no second pass or extra memory (table construction is amortised over all
-    // executes against the same generators, like msm_precompute in the reference).
-    Affine<C> a = XYZZ<C>::to_affine(q);
-    store_fp<F>(table, 2 * ((size_t)j * n + i), a.x);
-    store_fp<F>(table, 2 * ((size_t)j * n + i) + 1, a.y);
-    q = XYZZ<C>::from_affine(a);
+    const size_t slot = (size_t)j * n + i;
+    store_fp<F>(table, 2 * slot, q.x);
+    store_fp<F>(table, 2 * slot + 1, q.y);
+    store_fp<F>(scratch, 3 * slot, q.zz);
+    store_fp<F>(scratch, 3 * slot + 1, q.zzz);
+    store_fp<F>(scratch, 3 * slot + 2, prod);          // product of the ZZ*ZZZ of the powers before this one
+    prod = F::mul(prod, F::mul(q.zz, q.zzz));           // never zero: the group has odd order, no power is the identity
+  }
+  F inv = F::inverse(prod);
+  for (int j = nwin - 1; j >= 1; --j) {
+    const size_t slot = (size_t)j * n + i;
+    const F zz = load_fp<F>(scratch, 3 * slot), zzz = load_fp<F>(scratch, 3 * slot + 1), before = load_fp<F>(scratch, 3 * slot + 2);
+    const F inv_j = F::mul(inv, before);                // 1 / (zz * zzz)
+    inv = F::mul(inv, F::mul(zz, zzz));
+    const F x = F::mul(load_fp<F>(table, 2 * slot), F::mul(inv_j, zzz));      // X / ZZ
+    const F y = F::mul(load_fp<F>(table, 2 * slot + 1), F::mul(inv_j, zz));   // Y / ZZZ
+    store_fp<F>(table, 2 * slot, x);
+    store_fp<F>(table, 2 * slot + 1, y);
   }
 }
 
@@ -451,8 +473,10 @@ void table_build(plk_msm_table* t, const void* d_points, cudaStream_t st) {
   t->table.alloc((size_t)t->g.nwin * t->n * t->point_bytes);
   if (t->n == 0) return;
   unsigned blocks = (unsigned)((t->n + 127) / 128);
-  msm_table_kernel<C><<<blocks, 128, 0, st>>>(d_points, t->n, t->g.c, t->g.nwin, t->table.p);
+  DevBuf scratch((size_t)t->g.nwin * t->n * 3 * sizeof(F));      // (ZZ, ZZZ, prefix product) per power; freed after the build
+  msm_table_kernel<C><<<blocks, 128, 0, st>>>(d_points, t->n, t->g.c, t->g.nwin, t->table.p, scratch.p);
   PLK_LAUNCHED();
+  PLK_CUDA(cudaStreamSynchronize(st));
 }
 
 template <class C>

@@ -406,3 +406,35 @@ def test_domain_split_ntt_emulated_ranks(logn, world, inverse):
     got = ranks[0].natural_from_outputs(outs)
     torch.cuda.synchronize()
     assert torch.equal(got, want)
+
+
+def test_reentrancy_from_host_threads():
+    """The reference calls this layer from rayon workers (plonk_util.rs:173-189, halo.rs:119-123): concurrent
+    host threads against ONE table and ONE plan must each get the right answer."""
+    import threading
+    c = po.TWEEDLEDEE
+    f = po.TWEEDLEDUM_BASE
+    n = 3000
+    xy = rp.gen_points(c.cid, 33, n)
+    pre = pk.msm_precompute_affine(c.cid, xy, 11)
+    plan = pk.fft_precompute(f.fid, 4096)
+    jobs = []
+    for i in range(6):
+        S = mont_array(c.scalar, rand_scalars(c.scalar, 900 + i, n))
+        X = mont_array(f, rand_scalars(f, 950 + i, 4096))
+        jobs.append((S, X))
+    want = [(pk.msm_execute(pre, S), pk.fft_with_precomputation_power_of_2(X, plan)) for S, X in jobs]
+    got = [None] * len(jobs)
+
+    def work(i):
+        S, X = jobs[i]
+        for _ in range(3):
+            got[i] = (pk.msm_execute(pre, S), pk.fft_with_precomputation_power_of_2(X, plan))
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    for i in range(len(jobs)):
+        assert np.array_equal(got[i][0][0], want[i][0][0]) and got[i][0][1] == want[i][0][1]
+        assert np.array_equal(got[i][1], want[i][1])
