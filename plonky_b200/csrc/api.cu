@@ -36,6 +36,17 @@ static void ensure_ctx() {
   PLK_CUDA(cudaStreamCreateWithFlags(&t_ctx.stream, cudaStreamNonBlocking));
   t_ctx.device = dev;
 }
+void ensure_async_pool() {
+  static thread_local int done_for = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || done_for == dev) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long keep = ~0ull;            // never hand cached blocks back to the driver
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  done_for = dev;
+}
 cudaStream_t thread_stream() {
   ensure_ctx();
   return t_ctx.stream;

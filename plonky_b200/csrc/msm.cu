@@ -46,6 +46,19 @@ int pick_window(size_t n) {
   return c;
 }
 
+// variable base (msm_parallel): every window has its own buckets, so the reduction work is nwin * 2^c
+int pick_window_variable(size_t n) {
+  if (const char* e = getenv("PLK_MSM_WINDOW_VAR")) {
+    int c = atoi(e);
+    if (c >= 4 && c <= 20) return c;
+  }
+  int lg = log2_ceil(n ? n : 1);
+  int c = lg - 5;
+  if (c < 4) c = 4;
+  if (c > 14) c = 14;
+  return c;
+}
+
 // scratch of the stream `st` (created on first use)
 plk_msm_scratch* scratch_for(plk_msm_table* t, cudaStream_t st) {
   std::lock_guard<std::mutex> lk(t->mu);
@@ -56,6 +69,9 @@ plk_msm_scratch* scratch_for(plk_msm_table* t, cudaStream_t st) {
     t->max_tasks = entries / g.task + g.nb + 1;
     const size_t xyzz = 2 * t->point_bytes;
     auto* s = new plk_msm_scratch();
+    if (t->temporary)
+      for (plk::DevBuf* b : {&s->counts, &s->offsets, &s->task_off, &s->cursors, &s->sorted, &s->partials, &s->buckets, &s->ranges, &s->big_list})
+        b->set_async(st);
     try {
       s->counts.alloc((size_t)g.nb * 4);
       s->offsets.alloc(((size_t)g.nb + 1) * 4);
@@ -109,7 +125,7 @@ void run_batch(plk_msm_table* t, const char* d_scalars, size_t k, char* d_out_xy
   }
 }
 
-plk_msm_table* new_table(int curve, size_t n, unsigned w) {
+plk_msm_table* new_table(int curve, size_t n, unsigned w, bool variable = false) {
   const int bits = curve_scalar_bits(curve);
   if (bits < 0) fail(PLK_EINVAL, "unknown curve id");
   if (w < 1 || w > 32) fail(PLK_EINVAL, "window size out of range");
@@ -118,9 +134,11 @@ plk_msm_table* new_table(int curve, size_t n, unsigned w) {
   t->n = n;
   t->w = w;
   t->g.n = n;
-  t->g.c = pick_window(n);
+  t->g.variable = variable ? 1 : 0;
+  t->g.c = variable ? pick_window_variable(n) : pick_window(n);
   t->g.nwin = (bits + 1 + t->g.c - 1) / t->g.c;
-  t->g.nb = 1u << (t->g.c - 1);
+  t->g.nbw = 1u << (t->g.c - 1);
+  t->g.nb = variable ? t->g.nbw * (unsigned)t->g.nwin : t->g.nbw;
   // task size: aim at >= ~75 K accumulate threads (4 CTAs of 128 on each of the 148 SMs) so that small MSMs
   // still fill the machine; large ones use the full 64-entry tasks
   {
@@ -135,17 +153,23 @@ plk_msm_table* new_table(int curve, size_t n, unsigned w) {
 }
 
 // build from raw host points (projective or affine layout)
-void precompute_host(int curve, const uint64_t* pts, const uint8_t* zero, size_t n, unsigned w, int projective, plk_msm_table** out) {
+void precompute_host(int curve, const uint64_t* pts, const uint8_t* zero, size_t n, unsigned w, int projective, plk_msm_table** out,
+                     bool variable = false) {
   if (!out) fail(PLK_EINVAL, "NULL out");
   *out = nullptr;
   if (n && !pts) fail(PLK_EINVAL, "NULL points");
-  plk_msm_table* t = new_table(curve, n, w);
+  plk_msm_table* t = new_table(curve, n, w, variable);
   try {
     cudaStream_t st = thread_stream();
+    if (variable) {               // lives for one msm_parallel call on this thread's stream
+      t->temporary = true;
+      t->temp_stream = st;
+      t->table.set_async(st);
+    }
     const size_t L = curve_base_limbs64(curve);
     t->point_bytes = 2 * L * 8;
     const size_t raw_bytes = n * (projective ? 3 : 2) * L * 8;
-    DevBuf d_raw(raw_bytes), d_zero(n), d_aff(n * t->point_bytes);
+    DevBuf d_raw(raw_bytes, st), d_zero(n, st), d_aff(n * t->point_bytes, st);
     if (n) PLK_CUDA(cudaMemcpyAsync(d_raw.p, pts, raw_bytes, cudaMemcpyHostToDevice, st));
     if (n && zero) PLK_CUDA(cudaMemcpyAsync(d_zero.p, zero, n, cudaMemcpyHostToDevice, st));
     ops_for(curve)->import_points(d_raw.p, zero ? d_zero.as<unsigned char>() : nullptr, n, projective, d_aff.p, st);
@@ -220,8 +244,9 @@ int plk_msm_execute_batch(const plk_msm_table* t, const uint64_t* scalars, size_
 int plk_msm_parallel(int curve, const uint64_t* scalars, const uint64_t* points_xyz, const uint8_t* zero, size_t n, unsigned w,
                      uint64_t* out_xyz, uint8_t* out_zero) {
   return guarded([&] {
+    // variable base: no table of powers is built (the reference builds and discards one, curve_msm.rs:54-61)
     plk_msm_table* t = nullptr;
-    precompute_host(curve, points_xyz, zero, n, w, 1, &t);
+    precompute_host(curve, points_xyz, zero, n, w, 1, &t, true);
     try {
       execute_host(t, scalars, n, 1, out_xyz, out_zero);
     } catch (...) {
@@ -291,7 +316,7 @@ int plk_points_generate(int curve, uint64_t seed, size_t n, uint64_t* points_xy)
     if (curve_scalar_bits(curve) < 0) fail(PLK_EINVAL, "unknown curve id");
     cudaStream_t st = thread_stream();
     const size_t bytes = n * 2 * curve_base_limbs64(curve) * 8;
-    DevBuf d(bytes);
+    DevBuf d(bytes, st);
     ops_for(curve)->generate_points(seed, n, d.p, st);
     PLK_CUDA(cudaMemcpyAsync(points_xy, d.p, bytes, cudaMemcpyDeviceToHost, st));
     PLK_CUDA(cudaStreamSynchronize(st));
@@ -308,7 +333,7 @@ int plk_affine_multisummation(int curve, const uint64_t* points_xy, const uint8_
     if (n && !points_xy) fail(PLK_EINVAL, "NULL points");
     cudaStream_t st = thread_stream();
     const size_t L = curve_base_limbs64(curve);
-    DevBuf d_pts(n * 2 * L * 8), d_z(n), d_off((lists + 1) * 8), d_out(lists * 3 * L * 8), d_oz(lists);
+    DevBuf d_pts(n * 2 * L * 8, st), d_z(n, st), d_off((lists + 1) * 8, st), d_out(lists * 3 * L * 8, st), d_oz(lists, st);
     if (n) PLK_CUDA(cudaMemcpyAsync(d_pts.p, points_xy, n * 2 * L * 8, cudaMemcpyHostToDevice, st));
     if (n && zero) PLK_CUDA(cudaMemcpyAsync(d_z.p, zero, n, cudaMemcpyHostToDevice, st));
     PLK_CUDA(cudaMemcpyAsync(d_off.p, offsets, (lists + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -331,7 +356,7 @@ int plk_curve_mul(int curve, const uint64_t* points_xyz, const uint8_t* zero, co
     if (!points_xyz || !scalars || !out_xyz || !out_zero) fail(PLK_EINVAL, "NULL buffer");
     cudaStream_t st = thread_stream();
     const size_t L = curve_base_limbs64(curve);
-    DevBuf d_raw(n * 3 * L * 8), d_z(n), d_aff(n * 2 * L * 8), d_s(n * 32), d_out(n * 3 * L * 8), d_oz(n);
+    DevBuf d_raw(n * 3 * L * 8, st), d_z(n, st), d_aff(n * 2 * L * 8, st), d_s(n * 32, st), d_out(n * 3 * L * 8, st), d_oz(n, st);
     PLK_CUDA(cudaMemcpyAsync(d_raw.p, points_xyz, n * 3 * L * 8, cudaMemcpyHostToDevice, st));
     if (zero) PLK_CUDA(cudaMemcpyAsync(d_z.p, zero, n, cudaMemcpyHostToDevice, st));
     PLK_CUDA(cudaMemcpyAsync(d_s.p, scalars, n * 32, cudaMemcpyHostToDevice, st));
@@ -349,7 +374,7 @@ int plk_batch_to_affine(int curve, const uint64_t* points_xyz, const uint8_t* ze
     if (!points_xyz || !out_xy || !out_zero) fail(PLK_EINVAL, "NULL buffer");
     cudaStream_t st = thread_stream();
     const size_t L = curve_base_limbs64(curve);
-    DevBuf d_in(n * 3 * L * 8), d_z(n), d_out(n * 2 * L * 8), d_oz(n);
+    DevBuf d_in(n * 3 * L * 8, st), d_z(n, st), d_out(n * 2 * L * 8, st), d_oz(n, st);
     PLK_CUDA(cudaMemcpyAsync(d_in.p, points_xyz, n * 3 * L * 8, cudaMemcpyHostToDevice, st));
     if (zero) PLK_CUDA(cudaMemcpyAsync(d_z.p, zero, n, cudaMemcpyHostToDevice, st));
     ops_for(curve)->to_affine_batch(d_in.p, zero ? d_z.as<unsigned char>() : nullptr, n, d_out.p, d_oz.as<unsigned char>(), st);

@@ -47,9 +47,9 @@ __device__ __forceinline__ void for_each_digit(const SF& canon, const MsmGeom& g
     if (raw > halfw) {
       // digit = raw - 2^c (negative or, when raw == 2^c, zero), carry one into the next window
       carry = 1;
-      if (raw != full) f(j, full - raw - 1, true);
+      if (raw != full) f(j, (g.variable ? (unsigned)j * g.nbw : 0u) + (full - raw - 1), true);
     } else if (raw != 0) {
-      f(j, raw - 1, false);
+      f(j, (g.variable ? (unsigned)j * g.nbw : 0u) + (raw - 1), false);
     }
   }
 }
@@ -64,36 +64,46 @@ __global__ void msm_count_kernel(const uint4* __restrict__ scalars, MsmGeom g, u
 }
 
 // single CTA: offsets[b] = exclusive sum of counts, task_off[b] = exclusive sum of ceil(count / S);
-// offsets[nb] / task_off[nb] = totals; cursors[b] = offsets[b] (scatter positions)
+// offsets[nb] / task_off[nb] = totals; cursors[b] = offsets[b] (scatter positions).  1024 entries per
+// step: warp-shuffle scans, one shared-memory hop for the 32 warp totals.
 static __global__ void msm_scan_kernel(const unsigned* __restrict__ counts, unsigned nb, unsigned task, unsigned* __restrict__ offsets,
-                                unsigned* __restrict__ task_off, unsigned* __restrict__ cursors) {
-  __shared__ unsigned s_a[1024], s_b[1024];
+                                       unsigned* __restrict__ task_off, unsigned* __restrict__ cursors) {
+  __shared__ unsigned w_a[32], w_b[32];
   __shared__ unsigned carry_a, carry_b;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) { carry_a = 0; carry_b = 0; }
   __syncthreads();
   for (unsigned base = 0; base < nb; base += 1024) {
-    unsigned i = base + threadIdx.x;
-    unsigned ca = i < nb ? counts[i] : 0;
-    unsigned cb = (ca + task - 1) / task;
-    s_a[threadIdx.x] = ca;
-    s_b[threadIdx.x] = cb;
-    __syncthreads();
-    for (unsigned d = 1; d < 1024; d <<= 1) {
-      unsigned va = 0, vb = 0;
-      if (threadIdx.x >= d) { va = s_a[threadIdx.x - d]; vb = s_b[threadIdx.x - d]; }
-      __syncthreads();
-      s_a[threadIdx.x] += va;
-      s_b[threadIdx.x] += vb;
-      __syncthreads();
+    const unsigned i = base + threadIdx.x;
+    const unsigned ca = i < nb ? counts[i] : 0;
+    const unsigned cb = (ca + task - 1) / task;
+    unsigned sa = ca, sb = cb;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned ta = __shfl_up_sync(0xffffffffu, sa, d), tb = __shfl_up_sync(0xffffffffu, sb, d);
+      if (lane >= (unsigned)d) { sa += ta; sb += tb; }
     }
+    if (lane == 31) { w_a[warp] = sa; w_b[warp] = sb; }
+    __syncthreads();
+    if (warp == 0) {
+      unsigned ta = w_a[lane], tb = w_b[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned ua = __shfl_up_sync(0xffffffffu, ta, d), ub = __shfl_up_sync(0xffffffffu, tb, d);
+        if (lane >= (unsigned)d) { ta += ua; tb += ub; }
+      }
+      w_a[lane] = ta;       // inclusive scan of the warp totals
+      w_b[lane] = tb;
+    }
+    __syncthreads();
+    const unsigned pa = carry_a + (warp ? w_a[warp - 1] : 0), pb = carry_b + (warp ? w_b[warp - 1] : 0);
     if (i < nb) {
-      unsigned ea = carry_a + s_a[threadIdx.x] - ca;
-      offsets[i] = ea;
-      cursors[i] = ea;
-      task_off[i] = carry_b + s_b[threadIdx.x] - cb;
+      offsets[i] = pa + sa - ca;
+      cursors[i] = pa + sa - ca;
+      task_off[i] = pb + sb - cb;
     }
     __syncthreads();
-    if (threadIdx.x == 1023) { carry_a += s_a[1023]; carry_b += s_b[1023]; }
+    if (threadIdx.x == 0) { carry_a += w_a[31]; carry_b += w_b[31]; }
     __syncthreads();
   }
   if (threadIdx.x == 0) { offsets[nb] = carry_a; task_off[nb] = carry_b; }
@@ -109,7 +119,7 @@ __global__ void msm_scatter_kernel(const uint4* __restrict__ scalars, MsmGeom g,
   for_each_digit(s, g, [&](int j, unsigned b, bool negative) {
     unsigned pos = atomicAdd(&cursors[b], 1u);
     // entry = table slot (window-major: j * n + i) with the sign in bit 31 (n * nwin < 2^31 checked on host)
-    sorted[pos] = (unsigned)((unsigned long long)j * g.n + i) | (negative ? 0x80000000u : 0u);
+    sorted[pos] = (unsigned)(g.variable ? i : (unsigned long long)j * g.n + i) | (negative ? 0x80000000u : 0u);
   });
 }
 
@@ -220,7 +230,7 @@ __global__ void __launch_bounds__(256) msm_big_bucket_kernel(const void* __restr
 // bucket index b carries weight (b + 1).  Range [lo, lo + R): sum_b (b + 1) B_b =
 //   sum_b (b - lo + 1) B_b  (running sum, curve_msm.rs:149-154)  +  lo * sum_b B_b
 template <class C>
-__global__ void msm_range_kernel(const void* __restrict__ buckets, unsigned nb, void* __restrict__ range_out) {
+__global__ void msm_range_kernel(const void* __restrict__ buckets, unsigned nb, unsigned nbw, void* __restrict__ range_out) {
   const unsigned r = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
   const int ql = threadIdx.x & 3;
   const unsigned qmask = 0xFu << (threadIdx.x & 28);
@@ -233,7 +243,8 @@ __global__ void msm_range_kernel(const void* __restrict__ buckets, unsigned nb, 
     run = QuadXYZZ<C>::add(run, load_xyzz<C>(buckets, b), ql, qmask);
     sum = QuadXYZZ<C>::add(sum, run, ql, qmask);
   }
-  if (lo != 0 && !run.is_identity()) sum = QuadXYZZ<C>::add(sum, QuadXYZZ<C>::mul_u64(run, lo, ql, qmask), ql, qmask);
+  const unsigned wlo = lo & (nbw - 1);            // index inside its window's bucket set (ranges never straddle windows)
+  if (wlo != 0 && !run.is_identity()) sum = QuadXYZZ<C>::add(sum, QuadXYZZ<C>::mul_u64(run, wlo, ql, qmask), ql, qmask);
   if (ql == 0) store_xyzz<C>(range_out, r, sum);
 }
 
@@ -278,6 +289,34 @@ __global__ void msm_final_kernel(const void* __restrict__ in, unsigned count, vo
     if (out_xyz) {
       Affine<C> a = XYZZ<C>::to_affine_gcd(total);
       const bool z = total.is_identity();
+      F one = z ? F::zero() : F::one();
+      for (int i = 0; i < F::N; ++i) {
+        out_xyz[i] = a.x.l[i];
+        out_xyz[F::N + i] = a.y.l[i];
+        out_xyz[2 * F::N + i] = one.l[i];
+      }
+      *out_zero = z ? 1 : 0;
+    }
+  }
+}
+
+// variable base: result = sum_j 2^(c j) W_j (Horner from the top window: c doublings per step), one quad
+template <class C>
+__global__ void msm_window_combine_kernel(const void* __restrict__ window_sums, int nwin, int c, void* __restrict__ out_xyzz,
+                                          uint32_t* __restrict__ out_xyz, unsigned char* __restrict__ out_zero) {
+  typedef Fp<typename C::Base> F;
+  const int ql = threadIdx.x & 3;
+  const unsigned qmask = 0xFu;
+  XYZZ<C> acc = load_xyzz<C>(window_sums, nwin - 1);
+  for (int j = nwin - 2; j >= 0; --j) {
+    for (int k = 0; k < c; ++k) acc = QuadXYZZ<C>::dbl(acc, ql, qmask);
+    acc = QuadXYZZ<C>::add(acc, load_xyzz<C>(window_sums, j), ql, qmask);
+  }
+  if (threadIdx.x == 0) {
+    if (out_xyzz) store_xyzz<C>(out_xyzz, 0, acc);
+    if (out_xyz) {
+      Affine<C> a = XYZZ<C>::to_affine_gcd(acc);
+      const bool z = acc.is_identity();
       F one = z ? F::zero() : F::one();
       for (int i = 0; i < F::N; ++i) {
         out_xyz[i] = a.x.l[i];
@@ -470,10 +509,16 @@ template <class C>
 void table_build(plk_msm_table* t, const void* d_points, cudaStream_t st) {
   typedef Fp<typename C::Base> F;
   t->point_bytes = 2 * sizeof(F);
+  if (t->g.variable) {                       // msm_parallel: no powers are precomputed, the "table" is the point set
+    t->table.alloc((size_t)t->n * t->point_bytes);
+    if (t->n) PLK_CUDA(cudaMemcpyAsync(t->table.p, d_points, (size_t)t->n * t->point_bytes, cudaMemcpyDeviceToDevice, st));
+    PLK_CUDA(cudaStreamSynchronize(st));
+    return;
+  }
   t->table.alloc((size_t)t->g.nwin * t->n * t->point_bytes);
   if (t->n == 0) return;
   unsigned blocks = (unsigned)((t->n + 127) / 128);
-  DevBuf scratch((size_t)t->g.nwin * t->n * 3 * sizeof(F));      // (ZZ, ZZZ, prefix product) per power; freed after the build
+  DevBuf scratch((size_t)t->g.nwin * t->n * 3 * sizeof(F), st);  // (ZZ, ZZZ, prefix product) per power; freed after the build
   msm_table_kernel<C><<<blocks, 128, 0, st>>>(d_points, t->n, t->g.c, t->g.nwin, t->table.p, scratch.p);
   PLK_LAUNCHED();
   PLK_CUDA(cudaStreamSynchronize(st));
@@ -530,20 +575,35 @@ void execute_one(plk_msm_table* t, plk_msm_scratch* s, const void* d_scalars, vo
   PLK_LAUNCHED();
   s->timer.mark(st);
   const unsigned nranges = (g.nb + kRangeSize - 1) / kRangeSize;
-  msm_range_kernel<C><<<(4 * nranges + 63) / 64, 64, 0, st>>>(s->buckets.p, g.nb, s->ranges.p);
+  msm_range_kernel<C><<<(4 * nranges + 63) / 64, 64, 0, st>>>(s->buckets.p, g.nb, g.nbw, s->ranges.p);
   PLK_LAUNCHED();
   s->timer.mark(st);
-  // final: chunks of 8 -> <= 128 quads -> tree -> normalise (the chunk sums reuse the partials buffer)
   const void* fin = s->ranges.p;
   unsigned fcount = nranges;
-  while (fcount > 64) {
-    const unsigned chunk = (fcount + 63) / 64 < 8 ? (fcount + 63) / 64 : 8;
+  auto chunk_pass = [&](unsigned chunk) {
     const unsigned nout = (fcount + chunk - 1) / chunk;
-    msm_sum_chunks_kernel<C><<<(4 * nout + 63) / 64, 64, 0, st>>>(fin, fcount, chunk, s->partials.p);
+    void* dst = (fin == s->partials.p) ? s->buckets.p : s->partials.p;     // ping-pong between consumed buffers
+    msm_sum_chunks_kernel<C><<<(4 * nout + 63) / 64, 64, 0, st>>>(fin, fcount, chunk, dst);
     PLK_LAUNCHED();
-    fin = s->partials.p;
+    fin = dst;
     fcount = nout;
+  };
+  if (g.variable) {
+    // per-window sums (chunks never straddle a window: both sizes are powers of two), then Horner
+    unsigned per_window = g.nbw / kRangeSize;
+    while (per_window > 1) {
+      const unsigned chunk = per_window < 8 ? per_window : 8;
+      chunk_pass(chunk);
+      per_window /= chunk;
+    }
+    msm_window_combine_kernel<C><<<1, 4, 0, st>>>(fin, g.nwin, g.c, d_partial, reinterpret_cast<uint32_t*>(d_out_xyz),
+                                                  reinterpret_cast<unsigned char*>(d_out_zero));
+    PLK_LAUNCHED();
+    s->timer.mark(st);
+    return;
   }
+  // fixed base: chunks of 8 -> <= 64 quads -> tree -> normalise
+  while (fcount > 64) chunk_pass((fcount + 63) / 64 < 8 ? (fcount + 63) / 64 : 8);
   unsigned fquads = 1;
   while (fquads < fcount && fquads < 64) fquads <<= 1;
   msm_final_kernel<C><<<1, 4 * fquads, fquads * xyzz, st>>>(fin, fcount, d_partial, reinterpret_cast<uint32_t*>(d_out_xyz),

@@ -14,7 +14,9 @@ struct MsmGeom {
   unsigned long long n;     // terms
   int c;                    // window bits
   int nwin;                 // windows = ceil((BITS + 1) / c)
-  unsigned nb;              // buckets = 2^(c-1)
+  unsigned nb;              // buckets in total: nbw (fixed-base table: all windows share them) or nwin * nbw (variable base)
+  unsigned nbw;             // buckets per window = 2^(c-1)
+  int variable;             // 1: no table of powers, buckets per window, windows combined with doublings (msm_parallel)
   unsigned task;            // S: entries per accumulate task (power of two, <= kTaskSizeMax)
 };
 
@@ -36,6 +38,8 @@ struct plk_msm_table {
   size_t point_bytes = 64; // affine point
   plk::DevBuf table;            // nwin * n affine points, window-major
   size_t max_tasks = 0;
+  bool temporary = false;       // created and destroyed inside one call (msm_parallel): stream-ordered allocations
+  cudaStream_t temp_stream = nullptr;
   std::mutex mu;                // guards the pools below (not the execution)
   std::mutex batch_mu;          // serialises the fork/join enqueue of the batch entry points
   std::map<cudaStream_t, plk_msm_scratch*> scratch;   // keyed by the executing stream

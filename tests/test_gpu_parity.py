@@ -438,3 +438,25 @@ def test_reentrancy_from_host_threads():
     for i in range(len(jobs)):
         assert np.array_equal(got[i][0][0], want[i][0][0]) and got[i][0][1] == want[i][0][1]
         assert np.array_equal(got[i][1], want[i][1])
+
+
+@pytest.mark.parametrize("name,n", [("Tweedledee", 5000), ("Tweedledum", 37), ("Bls12377", 1200), ("Tweedledee", 1 << 15)])
+def test_msm_parallel_variable_base(name, n):
+    """msm_parallel(scalars, generators, w) (curve_msm.rs:54-61) through the table-free variable-base path:
+    per-window buckets + Horner over the windows; equals the closed form [sum s_i k_i] G and the port."""
+    c = po.CURVES[name]
+    seed = 4242
+    xy = rp.gen_points(c.cid, seed, n)
+    f = c.base
+    xyz = np.zeros((n, 3, f.limbs), dtype=np.uint64)
+    xyz[:, :2] = xy
+    xyz[:, 2] = ints_to_limbs([f.R], f.limbs)[0]
+    scalars = rand_scalars(c.scalar, 77, n)
+    scalars[0], scalars[1 % n] = 0, c.scalar.p - 1
+    S = mont_array(c.scalar, scalars)
+    out, oz = pk.msm_parallel(c.cid, S, xyz, 8)
+    ksum = sum(s * splitmix_hash(seed + i) for i, s in enumerate(scalars)) % c.scalar.p
+    assert result_point(c, out, oz) == c.mul(ksum, c.gen)
+    if n <= 5000:
+        ref_out, ref_zero = rp.MsmTable(c.cid, xy, None, 8).execute(S, parallel=True)
+        assert oz == ref_zero and np.array_equal(out[:2], ref_out)
