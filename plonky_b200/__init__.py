@@ -39,9 +39,20 @@ __all__ = [
 # ids of include/plonky_b200.h
 TWEEDLEDEE_BASE, TWEEDLEDUM_BASE, BLS12_377_SCALAR, BLS12_377_BASE = 0, 1, 2, 3
 TWEEDLEDEE, TWEEDLEDUM, BLS12_377 = 0, 1, 2
-FIELD_LIMBS = {0: 4, 1: 4, 2: 4, 3: 6}
-CURVE_BASE_FIELD = {0: 0, 1: 1, 2: 3}
-CURVE_SCALAR_FIELD = {0: 1, 1: 0, 2: 2}
+class _IdMap(dict):
+    """id -> value table whose misses are ValueError (unknown field / curve id), like PLK_EINVAL."""
+
+    def __init__(self, what, *a):
+        super().__init__(*a)
+        self.what = what
+
+    def __missing__(self, key):
+        raise ValueError(f"unknown {self.what} id {key!r}")
+
+
+FIELD_LIMBS = _IdMap("field", {0: 4, 1: 4, 2: 4, 3: 6})
+CURVE_BASE_FIELD = _IdMap("curve", {0: 0, 1: 1, 2: 3})
+CURVE_SCALAR_FIELD = _IdMap("curve", {0: 1, 1: 0, 2: 2})
 
 PLK_OK, PLK_EINVAL, PLK_ELENGTH, PLK_ENOTPOW2, PLK_ESIZE, PLK_EZERO, PLK_ECUDA, PLK_ENOMEM, PLK_ETOOBIG = range(9)
 

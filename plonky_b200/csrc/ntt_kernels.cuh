@@ -214,8 +214,10 @@ __device__ __noinline__ void ntt_post_factors(const NttPassParams& p, const Tile
   __syncthreads();
 }
 
-template <class F>
-__global__ void __launch_bounds__(kNttThreads, 2) ntt_pass_kernel(NttPassParams p) {
+// MAXQ = 3: radix-8 register rounds, 2 CTAs per SM (128 registers).  MAXQ = 2: radix-4 rounds, 3 CTAs per SM
+// (85 registers): more shared-memory round trips, more warps to hide them behind.
+template <class F, int MAXQ>
+__global__ void __launch_bounds__(kNttThreads, MAXQ == 3 ? 2 : 3) ntt_pass_kernel(NttPassParams p) {
   extern __shared__ uint4 smem[];
   constexpr int PIECES = F::N / 4;
   const int T = 1 << p.log_t, R = 1 << p.r, elems = R * T;
@@ -268,12 +270,12 @@ __global__ void __launch_bounds__(kNttThreads, 2) ntt_pass_kernel(NttPassParams 
   {
     int l0 = 0;
     const int r = p.r;
-    if (r >= 3) { ntt_round<F, 3, true>(p, smem, wsub_s, 0); l0 = 3; }
-    else if (r == 2) { ntt_round<F, 2, true>(p, smem, wsub_s, 0); l0 = 2; }
+    if (MAXQ >= 3 && r >= 3) { ntt_round<F, (MAXQ >= 3 ? 3 : 2), true>(p, smem, wsub_s, 0); l0 = 3; }
+    else if (r >= 2) { ntt_round<F, 2, true>(p, smem, wsub_s, 0); l0 = 2; }
     else if (r == 1) { ntt_round<F, 1, true>(p, smem, wsub_s, 0); l0 = 1; }
     while (l0 < r) {
-      const int q = (r - l0 >= 3) ? 3 : (r - l0);
-      if (q == 3) ntt_round<F, 3, false>(p, smem, wsub_s, l0);
+      const int q = (r - l0 >= MAXQ) ? MAXQ : (r - l0);
+      if (MAXQ >= 3 && q == 3) ntt_round<F, (MAXQ >= 3 ? 3 : 2), false>(p, smem, wsub_s, l0);
       else if (q == 2) ntt_round<F, 2, false>(p, smem, wsub_s, l0);
       else ntt_round<F, 1, false>(p, smem, wsub_s, l0);
       l0 += q;
