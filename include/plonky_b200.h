@@ -189,7 +189,8 @@ int plk_fft_dist_phase_b(const plk_fft_plan* plan_n, void* d_recv, unsigned log_
  * Helpers on the same arithmetic (used by the parity tests and by callers that stay on device)
  * ---------------------------------------------------------------------------------------- */
 /* elementwise field ops over n elements (src/field/monty.rs:38-177):
- * 0 add, 1 sub, 2 mul, 3 square, 4 neg, 5 inverse, 6 to_canonical, 7 from_canonical, 8 double */
+ * 0 add, 1 sub, 2 mul, 3 square, 4 neg, 5 inverse (Fermat ladder), 6 to_canonical, 7 from_canonical, 8 double,
+ * 9 inverse by the binary extended GCD (the reference's algorithm, src/bigint/bigint_inverse.rs:6-55) */
 int plk_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
 /* Field::batch_multiplicative_inverse (src/field/field.rs:251-278); PLK_EZERO if any input is 0 */
 int plk_batch_inverse(int field, const uint64_t* in, uint64_t* out, size_t n);

@@ -406,7 +406,7 @@ def divide_by_z_h(coefficients, n_gates: int, precomputation: FftPrecomputation)
 # ------------------------------------------------------------------------------------------------
 # helpers on the same arithmetic
 # ------------------------------------------------------------------------------------------------
-_OPS = dict(add=0, sub=1, mul=2, square=3, neg=4, inverse=5, to_canonical=6, from_canonical=7, double=8)
+_OPS = dict(add=0, sub=1, mul=2, square=3, neg=4, inverse=5, to_canonical=6, from_canonical=7, double=8, inverse_gcd=9)
 
 
 def field_op(field: int, op: str, a, b=None) -> np.ndarray:

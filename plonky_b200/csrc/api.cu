@@ -79,6 +79,7 @@ __global__ void field_op_kernel(int op, const void* a, const void* b, void* out,
     case 5: r = F::inverse(x); break;
     case 6: r = F::to_canonical(x); break;
     case 7: r = F::from_canonical(x); break;
+    case 9: r = F::inverse_gcd(x); break;
     default: r = F::dbl(x); break;
   }
   store_fp<F>(out, i, r);
@@ -200,7 +201,7 @@ int plk_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64
   return guarded([&] {
     const int L = plk_field_limbs(field);
     if (!L) fail(PLK_EINVAL, "unknown field id");
-    if (op < 0 || op > 8) fail(PLK_EINVAL, "unknown op");
+    if (op < 0 || op > 9) fail(PLK_EINVAL, "unknown op");
     if (n == 0) return;
     if (!a || !out || ((op <= 2) && !b)) fail(PLK_EINVAL, "NULL buffer");
     cudaStream_t st = thread_stream();
@@ -210,7 +211,7 @@ int plk_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64
     void* dout = thread_scratch(2, bytes);
     PLK_CUDA(cudaMemcpyAsync(da, a, bytes, cudaMemcpyHostToDevice, st));
     if (b) PLK_CUDA(cudaMemcpyAsync(db, b, bytes, cudaMemcpyHostToDevice, st));
-    if (op == 5) {
+    if (op == 5 || op == 9) {
       // inverse of zero is an error in the reference (field.rs:159-165 returns None, Div panics)
       for (size_t i = 0; i < n; ++i) {
         bool z = true;

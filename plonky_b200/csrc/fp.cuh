@@ -293,14 +293,55 @@ struct Fp {
 #pragma unroll
     for (int i = 0; i < N; ++i) { u[i] = a.l[i]; v[i] = P::mod(i); b[i] = 0; c[i] = 0; }
     b[0] = 1;
-    auto is_one = [](const uint32_t (&x)[N]) { uint32_t acc = x[0] ^ 1u; for (int i = 1; i < N; ++i) acc |= x[i]; return acc == 0; };
-    auto shr1 = [](uint32_t (&x)[N]) { for (int i = 0; i < N - 1; ++i) x[i] = (x[i] >> 1) | (x[i + 1] << 31); x[N - 1] >>= 1; };
-    auto add_p = [](uint32_t (&x)[N]) { uint64_t cy = 0; for (int i = 0; i < N; ++i) { cy += (uint64_t)x[i] + P::mod(i); x[i] = (uint32_t)cy; cy >>= 32; } };
-    auto less = [](const uint32_t (&x)[N], const uint32_t (&y)[N]) { for (int i = N - 1; i >= 0; --i) { if (x[i] != y[i]) return x[i] < y[i]; } return false; };
-    auto sub = [](uint32_t (&x)[N], const uint32_t (&y)[N]) { uint64_t bw = 0; for (int i = 0; i < N; ++i) { uint64_t t = (uint64_t)x[i] - y[i] - bw; x[i] = (uint32_t)t; bw = (t >> 63) & 1; } };
+    // (every loop below has a compile-time trip count and is unrolled, so u, v, b, c stay in registers)
+    auto is_one = [](const uint32_t (&x)[N]) {
+      uint32_t acc = x[0] ^ 1u;
+#pragma unroll
+      for (int i = 1; i < N; ++i) acc |= x[i];
+      return acc == 0;
+    };
+    auto shr = [](uint32_t (&x)[N], int k) {           // 1 <= k <= 31
+#pragma unroll
+      for (int i = 0; i < N - 1; ++i) x[i] = (x[i] >> k) | (x[i + 1] << (32 - k));
+      x[N - 1] >>= k;
+    };
+    // x <- x / 2^k mod p for 1 <= k <= 31: add the multiple m p that clears the low k bits (p == 1 mod 2^32, so
+    // m = -x mod 2^k), then shift.  x < p and m < 2^31 keep x + m p below 2^(32 N + 31): one extra limb.
+    auto div_pow2 = [&shr](uint32_t (&x)[N], int k) {
+      const uint32_t m = (0u - x[0]) & ((1u << k) - 1u);
+      uint64_t cy = 0;
+      uint32_t top;
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        cy += (uint64_t)m * P::mod(i) + x[i];
+        x[i] = (uint32_t)cy;
+        cy >>= 32;
+      }
+      top = (uint32_t)cy;
+      shr(x, k);
+      x[N - 1] |= top << (32 - k);
+    };
+    auto less = [](const uint32_t (&x)[N], const uint32_t (&y)[N]) {
+      bool lt = false;
+#pragma unroll
+      for (int i = 0; i < N; ++i) lt = (x[i] < y[i]) || (x[i] == y[i] && lt);      // most significant limb decides last
+      return lt;
+    };
+    auto add_p = [](uint32_t (&x)[N]) {
+      uint64_t cy = 0;
+#pragma unroll
+      for (int i = 0; i < N; ++i) { cy += (uint64_t)x[i] + P::mod(i); x[i] = (uint32_t)cy; cy >>= 32; }
+    };
+    auto sub = [](uint32_t (&x)[N], const uint32_t (&y)[N]) {
+      uint64_t bw = 0;
+#pragma unroll
+      for (int i = 0; i < N; ++i) { uint64_t t = (uint64_t)x[i] - y[i] - bw; x[i] = (uint32_t)t; bw = (t >> 63) & 1; }
+    };
+    auto ctz31 = [](uint32_t w) { int k = 0; while (k < 31 && !((w >> k) & 1)) ++k; return k; };   // w != 0 in practice; capped at 31
     while (!is_one(u) && !is_one(v)) {
-      while (!(u[0] & 1)) { shr1(u); if (b[0] & 1) add_p(b); shr1(b); }
-      while (!(v[0] & 1)) { shr1(v); if (c[0] & 1) add_p(c); shr1(c); }
+      // strip the trailing zero bits of u (resp. v) in one go, dividing b (resp. c) by the same power of two
+      while (!(u[0] & 1)) { const int k = u[0] ? ctz31(u[0]) : 31; shr(u, k); div_pow2(b, k); }
+      while (!(v[0] & 1)) { const int k = v[0] ? ctz31(v[0]) : 31; shr(v, k); div_pow2(c, k); }
       if (less(u, v)) { sub(v, u); if (less(c, b)) add_p(c); sub(c, b); }
       else { sub(u, v); if (less(b, c)) add_p(b); sub(b, c); }
     }

@@ -55,6 +55,7 @@ def test_field_ops(name):
     assert canon_list(f, pk.field_op(f.fid, "double", V)) == [2 * x % f.p for x in vals]
     nz = [x for x in vals if x]
     assert canon_list(f, pk.field_op(f.fid, "inverse", mont_array(f, nz))) == [f.inv(x) for x in nz]
+    assert canon_list(f, pk.field_op(f.fid, "inverse_gcd", mont_array(f, nz))) == [f.inv(x) for x in nz]
     raw = ints_to_limbs(vals, f.limbs)
     m = pk.field_op(f.fid, "from_canonical", raw)
     assert limbs_to_ints(m) == [f.to_mont(x) for x in vals]
