@@ -51,6 +51,28 @@ void plan_build(plk_fft_plan* pl) {
     build_pow_table<P>(wn, pl->lo_bits, (size_t)1 << (L - pl->lo_bits), nullptr, pl->tw_hi[inv], st);
     if (inv) build_pow_table<P>(wn, pl->lo_bits, (size_t)1 << (L - pl->lo_bits), pl->n_inv.p, pl->tw_hi_inv_scaled, st);
   }
+  // direct twiddle tables for the in-place passes with a small N_d (digit d is processed with M_d = 2^(r_{d+1}+..+r_m))
+  {
+    int log_m_acc = pl->dig[pl->m - 1];
+    for (int d = pl->m - 2; d >= 0; --d) {
+      const int r = pl->dig[d], log_nd = r + log_m_acc, sh = L - log_nd;
+      static const int direct_log = getenv("PLK_NTT_DIRECT_LOG") ? atoi(getenv("PLK_NTT_DIRECT_LOG")) : kDirectLog;
+      if (log_nd <= direct_log && !getenv("PLK_NTT_NO_DIRECT")) {
+        const size_t cnt = (size_t)1 << log_nd;
+        const unsigned blocks = (unsigned)((cnt + 127) / 128);
+        for (int v = 0; v < 3; ++v) {
+          if (v == 2 && d != 0) continue;                  // the scaled table only serves the last pass (digit 1) ...
+          if (v == 1 && d == 0) continue;                  // ... which never uses the unscaled inverse one
+          pl->direct[v][d].alloc(cnt * sizeof(F));
+          const int inv = v ? 1 : 0;
+          direct_twiddle_kernel<F><<<blocks, 128, 0, st>>>(pl->tw_lo[inv].p, v == 2 ? pl->tw_hi_inv_scaled.p : pl->tw_hi[inv].p, pl->lo_bits,
+                                                       log_m_acc, r, sh, v == 2 ? 1 : 0, pl->direct[v][d].template as<F>());
+          PLK_LAUNCHED();
+        }
+      }
+      log_m_acc += r;
+    }
+  }
   PLK_CUDA(cudaStreamSynchronize(st));
 }
 
@@ -109,6 +131,8 @@ void run_ntt(const plk_fft_plan* pl, const void* d_in, size_t n_in, size_t in_st
       p.log_m = log_m_acc;
       p.log_t = p.log_m < tile_log ? p.log_m : tile_log;
       if (inverse && p.last) { p.tw_all = 1; p.tw_hi = pl->tw_hi_inv_scaled.p; }
+      const int v = (inverse && p.last) ? 2 : inv;
+      if (pl->direct[v][d].p) p.tw_direct = pl->direct[v][d].p;
     }
     if (p.last) {
       p.post_lo = ops.post_lo;

@@ -51,6 +51,7 @@ struct NttPassParams {
   const void* tw_hi;              // w_n^(e << lo_bits)
   int lo_bits;
   int tw_all;                     // also multiply row 0 (n^-1 folded into tw_hi)
+  const void* tw_direct;          // optional full table w_{N_d}^(j_d k'') at [(j_d << log_m) + k''] (small N_d): one load, one product
   const void* pre_lo;             // optional input multiplier s^j (two-level, same lo_bits)
   const void* pre_hi;
   const void* post_lo;            // optional output multiplier s^k (two-level)
@@ -184,6 +185,9 @@ __device__ __noinline__ void ntt_pre_factors(const NttPassParams& p, const TileG
       const unsigned long long kk = g.k0 + col;
       const unsigned long long ex = ((unsigned long long)orow * kk) << (p.log_n - p.r - p.log_m);
       if (p.tw_none) { }
+      else if (p.tw_direct) {
+        if (p.tw_all || ex != 0) { fac = load_fp<F>(p.tw_direct, ((size_t)orow << p.log_m) + (size_t)kk); have = true; }
+      }
       else if (p.tw_all) { fac = two_level_always<F>(p.tw_lo, p.tw_hi, p.lo_bits, ex); have = true; }
       else if (ex != 0) { fac = two_level<F>(p.tw_lo, p.tw_hi, p.lo_bits, ex); have = true; }
     }
@@ -332,6 +336,17 @@ __global__ void pow_table_kernel(F base, unsigned long long stride_log2, unsigne
   }
   if (scale) acc = F::mul(acc, *scale);
   out[i] = acc;
+}
+
+// full inter-pass twiddle table of one in-place pass: out[(j << log_m) + k] = w_n^((j k) << sh) (times the
+// folded scale when hi is the scaled table)
+template <class F>
+__global__ void direct_twiddle_kernel(const void* lo, const void* hi, int lo_bits, int log_m, int r, int sh, int always, F* out) {
+  const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (i >= (1ull << (log_m + r))) return;
+  const unsigned long long j = i >> log_m, kk = i & ((1ull << log_m) - 1);
+  const unsigned long long ex = (j * kk) << sh;
+  out[i] = always ? two_level_always<F>(lo, hi, lo_bits, ex) : two_level<F>(lo, hi, lo_bits, ex);
 }
 
 // denominators of divide_by_z_h (src/polynomial.rs:351-361): tbl[i] = 1 / (g^n * w^(n i) - 1), i < period

@@ -10,6 +10,8 @@ constexpr int kSubLog = 8;          // largest sub-transform: 2^8 rows
 constexpr int kMaxDigits = 6;       // 6 * 8 = 48 >= largest TWO_ADICITY (47)
 constexpr int kTileColsLog = 3;     // 8 columns per tile
 constexpr int kNttThreads = 256;
+constexpr int kDirectLog = 24;      // passes with N_d <= 2^24 read their inter-pass twiddles from a full table (<= 512 MiB each;
+                                    // PLK_NTT_DIRECT_LOG lowers it, larger passes fall back to two small tables + one product)
 }  // namespace plk
 
 struct CosetTables {
@@ -29,6 +31,9 @@ struct plk_fft_plan {
   plk::DevBuf wsub[2];            // [0] forward, [1] inverse
   plk::DevBuf tw_lo[2], tw_hi[2];
   plk::DevBuf tw_hi_inv_scaled;   // inverse hi table with n^-1 folded in
+  // full twiddle tables of the in-place passes whose N_d = R_d M_d is small (<= 2^kDirectLog entries):
+  // [0] forward, [1] inverse, [2] inverse with n^-1 folded (last pass); indexed by digit
+  plk::DevBuf direct[3][plk::kMaxDigits];
   plk::DevBuf n_inv;              // one element: n^-1
   plk::DevBuf pow2_inv;           // 2^-k, k <= TWO_ADICITY
   std::mutex mu;
