@@ -138,8 +138,8 @@ struct TileGeom {
   unsigned long long k0;      // in-place: k'' of column 0 ; first: jlow of column 0
 };
 
-template <class F, int Q, bool LAYER0>
-__device__ __forceinline__ void ntt_round(const NttPassParams& p, uint4* smem, const uint4* wsub, int l0) {
+template <class F, int Q, bool LAYER0, bool FUSE_TW = false>
+__device__ __forceinline__ void ntt_round(const NttPassParams& p, uint4* smem, const uint4* wsub, int l0, unsigned long long k0 = 0) {
   const int T = 1 << p.log_t, elems = 1 << (p.r + p.log_t);
   const int groups = elems >> Q;
   for (int gi = threadIdx.x; gi < groups; gi += blockDim.x) {
@@ -152,6 +152,16 @@ __device__ __forceinline__ void ntt_round(const NttPassParams& p, uint4* smem, c
     for (int e = 0; e < (1 << Q); ++e) {
       const int row = base_row + (e << l0);
       x[e] = lds_fp<F>(smem, elems, row * T + (col ^ (row & (T - 1))));
+    }
+    if (FUSE_TW) {
+      // inter-pass twiddle from the full table, folded into the first register round (l0 == 0; rows sit at
+      // their bit-reversed position): no separate shared-memory pass, no extra barrier
+      const size_t kk = (size_t)(k0 + col);
+#pragma unroll
+      for (int e = 0; e < (1 << Q); ++e) {
+        const size_t orow = bitrev((unsigned)(base_row + e), p.r);
+        if (p.tw_all || (orow != 0 && kk != 0)) x[e] = F::mul(x[e], load_fp<F>(p.tw_direct, (orow << p.log_m) + kk));
+      }
     }
     dit_layers<F, Q, LAYER0>(x, l0, low, wsub);
 #pragma unroll
@@ -270,12 +280,17 @@ __global__ void __launch_bounds__(kNttThreads, MAXQ == 3 ? 2 : 3) ntt_pass_kerne
   __syncthreads();
 
   // ---- input-side factors, then butterflies as radix-8 / 4 / 2 register rounds ----
-  if ((p.first && p.pre_lo) || (!p.first && !p.tw_none) || p.scale) ntt_pre_factors<F>(p, g, smem);
+  const bool fuse_tw = MAXQ == 2 && !p.first && !p.tw_none && !p.scale && p.tw_direct && p.r >= 2;
+  if (!fuse_tw && ((p.first && p.pre_lo) || (!p.first && !p.tw_none) || p.scale)) ntt_pre_factors<F>(p, g, smem);
   {
     int l0 = 0;
     const int r = p.r;
     if (MAXQ >= 3 && r >= 3) { ntt_round<F, (MAXQ >= 3 ? 3 : 2), true>(p, smem, wsub_s, 0); l0 = 3; }
-    else if (r >= 2) { ntt_round<F, 2, true>(p, smem, wsub_s, 0); l0 = 2; }
+    else if (r >= 2) {
+      if (fuse_tw) ntt_round<F, 2, true, true>(p, smem, wsub_s, 0, g.k0);
+      else ntt_round<F, 2, true>(p, smem, wsub_s, 0);
+      l0 = 2;
+    }
     else if (r == 1) { ntt_round<F, 1, true>(p, smem, wsub_s, 0); l0 = 1; }
     while (l0 < r) {
       const int q = (r - l0 >= MAXQ) ? MAXQ : (r - l0);
