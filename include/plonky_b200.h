@@ -215,6 +215,31 @@ int plk_points_generate(int curve, uint64_t seed, size_t n, uint64_t* points_xy)
 int plk_msm_precompute_affine_dev(int curve, const void* d_points_xy, size_t n, unsigned w,
                                   plk_msm_table** out);
 
+/* ------------------------------------------------------------------------------------------
+ * Halo inner-product argument rounds  (src/halo.rs:63-124, the loop of batch_opening_proof)
+ * ---------------------------------------------------------------------------------------- */
+/* halo_a, halo_b (n scalar-field elements each) and halo_g (n points) kept in HBM across the log2(n) rounds
+ * (halo.rs:53-57).  The challenger (Rescue sponge), the blinding terms [l_j] H / [r_j] H and the
+ * [<a, b>] U' terms stay with the caller (plk_curve_mul covers the single scalar multiplications). */
+typedef struct plk_ipa_state plk_ipa_state;
+/* a, b: n*4 limbs (Montgomery); g_xy: n affine points (2*L limbs each) + optional zero flags.  n must be a power
+ * of two (PLK_ENOTPOW2 = log2_strict(degree), halo.rs:62). */
+int plk_ipa_new(int curve, const uint64_t* a, const uint64_t* b, const uint64_t* g_xy, const uint8_t* g_zero,
+                size_t n, plk_ipa_state** out);
+size_t plk_ipa_len(const plk_ipa_state* s);     /* current vector length (halves with every fold) */
+void plk_ipa_free(plk_ipa_state* s);
+/* First half of a round (halo.rs:87-93): out_l = msm_parallel(a_lo, G_hi, 8), out_r = msm_parallel(a_hi, G_lo, 8)
+ * as normalised projective points (3*L limbs + zero flag), out_ip_l = <a_lo, b_hi>, out_ip_r = <a_hi, b_lo>
+ * (Field::inner_product, src/field/field.rs:214-221; 4 limbs each).  PLK_EINVAL once the length is 1. */
+int plk_ipa_round_lr(plk_ipa_state* s, uint64_t* out_l_xyz, uint8_t* out_l_zero, uint64_t* out_r_xyz,
+                     uint8_t* out_r_zero, uint64_t* out_ip_l, uint64_t* out_ip_r);
+/* Second half (halo.rs:117-123) with the round challenge u = u_j and u_inv = u_j^-1 (4 limbs each):
+ * a <- u_inv a_hi + u a_lo, b <- u_inv b_lo + u b_hi, G_i <- msm_parallel([u_inv, u], [G_lo_i, G_hi_i], 4). */
+int plk_ipa_fold(plk_ipa_state* s, const uint64_t* u, const uint64_t* u_inv);
+/* Copy the current vectors out (any pointer may be NULL): after the last fold these are halo_a[0], halo_b[0]
+ * and halo_g[0].to_affine() (halo.rs:126-131).  g_xy: len*2*L limbs, g_zero: len bytes. */
+int plk_ipa_read(const plk_ipa_state* s, uint64_t* a, uint64_t* b, uint64_t* g_xy, uint8_t* g_zero);
+
 /* number of CUDA kernels this library has launched in the calling process (bench.py: gpu_launches) */
 uint64_t plk_kernel_launch_count(void);
 

@@ -466,6 +466,35 @@ def divide_by_z_h(field: Field, a: Sequence[int], n: int) -> List[int]:
 # --------------------------------------------------------------------------------------
 # Deterministic synthetic inputs; shared by tests and bench.
 # --------------------------------------------------------------------------------------
+# ---------------------------------------------------------------------------------------------
+# src/halo.rs:63-124 -- one round of the Halo inner-product argument on canonical ints / affine points
+# (without the blinding and U' terms, which are single scalar multiplications added by the caller)
+# ---------------------------------------------------------------------------------------------
+def halo_round_lr(curve: Curve, a: Sequence[int], b: Sequence[int], g: Sequence[Affine]):
+    """(<a_lo, G_hi>, <a_hi, G_lo>, <a_lo, b_hi>, <a_hi, b_lo>)  -- halo.rs:87-93"""
+    n = len(a)
+    log2_strict(n)
+    assert len(b) == n and len(g) == n                      # debug_assert_eq!, halo.rs:67-69
+    m = n // 2
+    q = curve.scalar.p
+    l = curve.msm_naive(a[:m], g[m:])
+    r = curve.msm_naive(a[m:], g[:m])
+    ip_l = sum(x * y for x, y in zip(a[:m], b[m:])) % q     # Field::inner_product, field.rs:214-221
+    ip_r = sum(x * y for x, y in zip(a[m:], b[:m])) % q
+    return l, r, ip_l, ip_r
+
+
+def halo_fold(curve: Curve, a: Sequence[int], b: Sequence[int], g: Sequence[Affine], u: int, u_inv: int):
+    """halo.rs:117-123: (u^-1 a_hi + u a_lo, u^-1 b_lo + u b_hi, [u^-1] G_lo + [u] G_hi)"""
+    n = len(a)
+    m = n // 2
+    q = curve.scalar.p
+    na = [(u_inv * a[m + i] + u * a[i]) % q for i in range(m)]
+    nb = [(u_inv * b[i] + u * b[m + i]) % q for i in range(m)]
+    ng = [curve.add(curve.mul(u_inv, g[i]), curve.mul(u, g[m + i])) for i in range(m)]
+    return na, nb, ng
+
+
 class SplitMix64:
     def __init__(self, seed: int):
         self.s = seed & MASK64

@@ -847,3 +847,81 @@ extern "C" int ref_to_digits(int cid, const uint64_t* scalar, int w, uint32_t* o
   }
   return -1;
 }
+
+// ------------------------------------------------------------------------------------------
+// src/halo.rs:63-124 -- one round of the Halo inner-product argument (the parts that touch the L1 kernels).
+// The challenger (Rescue sponge), the blinding terms [l_j] H and the U' terms are the caller's: they are not
+// data parallel.  msm_parallel(scalars, generators, w) = msm_precompute + msm_execute_parallel (curve_msm.rs:54-61).
+// ------------------------------------------------------------------------------------------
+template <class C> static Proj<C> msm_parallel(const std::vector<Fe<typename C::Scalar>>& sc, const std::vector<Proj<C>>& gens, int w) {
+  MsmPre<C>* pre = msm_precompute<C>(gens, w);
+  Proj<C> r = msm_execute_parallel(*pre, sc);
+  delete pre;
+  return r;
+}
+// halo.rs:87-93: <a_lo, G_hi>, <a_hi, G_lo> (window_size = 8, :78) and the inner products <a_lo, b_hi>, <a_hi, b_lo>
+template <class C> static int ipa_round_lr_t(const uint64_t* a, const uint64_t* b, const uint64_t* g_xy, const uint8_t* g_zero, size_t n,
+                                             uint64_t* out_lr_xy, uint8_t* out_lr_zero, uint64_t* out_ip) {
+  typedef Fe<typename C::Scalar> S;
+  const size_t mid = n / 2;
+  auto g = load_affine<C>(g_xy, g_zero, n);
+  std::vector<S> av(n), bv(n);
+  for (size_t i = 0; i < n; ++i) { av[i] = S::from_limbs(a + i * S::N); bv[i] = S::from_limbs(b + i * S::N); }
+  std::vector<Proj<C>> g_lo(mid), g_hi(mid);
+  for (size_t i = 0; i < mid; ++i) { g_lo[i] = to_proj(g[i]); g_hi[i] = to_proj(g[mid + i]); }
+  std::vector<S> a_lo(av.begin(), av.begin() + mid), a_hi(av.begin() + mid, av.end());
+  Proj<C> l = msm_parallel<C>(a_lo, g_hi, 8), r = msm_parallel<C>(a_hi, g_lo, 8);
+  store_affine(to_affine(l), out_lr_xy, out_lr_zero);
+  store_affine(to_affine(r), out_lr_xy + 2 * C::Base::N, out_lr_zero + 1);
+  S ip_l = S::zero(), ip_r = S::zero();           // Field::inner_product, field.rs:214-221
+  for (size_t i = 0; i < mid; ++i) { ip_l = ip_l + av[i] * bv[mid + i]; ip_r = ip_r + av[mid + i] * bv[i]; }
+  memcpy(out_ip, ip_l.v.l, 8 * S::N);
+  memcpy(out_ip + S::N, ip_r.v.l, 8 * S::N);
+  return 0;
+}
+// halo.rs:117-123: a' = u^-1 a_hi + u a_lo, b' = u^-1 b_lo + u b_hi, G'_i = msm_parallel([u^-1, u], [G_lo_i, G_hi_i], 4)
+template <class C> static int ipa_fold_t(const uint64_t* a, const uint64_t* b, const uint64_t* g_xy, const uint8_t* g_zero, size_t n,
+                                         const uint64_t* u_limbs, const uint64_t* u_inv_limbs, uint64_t* out_a, uint64_t* out_b,
+                                         uint64_t* out_g_xy, uint8_t* out_g_zero) {
+  typedef Fe<typename C::Scalar> S;
+  const size_t mid = n / 2;
+  const S u = S::from_limbs(u_limbs), u_inv = S::from_limbs(u_inv_limbs);
+  auto g = load_affine<C>(g_xy, g_zero, n);
+  for (size_t i = 0; i < mid; ++i) {
+    S a_lo = S::from_limbs(a + i * S::N), a_hi = S::from_limbs(a + (mid + i) * S::N);
+    S b_lo = S::from_limbs(b + i * S::N), b_hi = S::from_limbs(b + (mid + i) * S::N);
+    S na = u_inv * a_hi + u * a_lo, nb = u_inv * b_lo + u * b_hi;
+    memcpy(out_a + i * S::N, na.v.l, 8 * S::N);
+    memcpy(out_b + i * S::N, nb.v.l, 8 * S::N);
+  }
+#pragma omp parallel for schedule(dynamic, 8)
+  for (long i = 0; i < (long)mid; ++i) {
+    std::vector<S> sc = {u_inv, u};
+    std::vector<Proj<C>> pts = {to_proj(g[i]), to_proj(g[mid + i])};
+    Proj<C> r = msm_parallel<C>(sc, pts, 4);
+    store_affine(to_affine(r), out_g_xy + 2 * i * C::Base::N, out_g_zero + i);
+  }
+  return 0;
+}
+extern "C" {
+int ref_ipa_round_lr(int cid, const uint64_t* a, const uint64_t* b, const uint64_t* g_xy, const uint8_t* g_zero, size_t n,
+                     uint64_t* out_lr_xy, uint8_t* out_lr_zero, uint64_t* out_ip) {
+  if (n < 2 || (n & (n - 1))) return -2;          // log2_strict(degree), halo.rs:62
+  switch (cid) {
+    case 0: return ipa_round_lr_t<Tweedledee>(a, b, g_xy, g_zero, n, out_lr_xy, out_lr_zero, out_ip);
+    case 1: return ipa_round_lr_t<Tweedledum>(a, b, g_xy, g_zero, n, out_lr_xy, out_lr_zero, out_ip);
+    case 2: return ipa_round_lr_t<Bls12377>(a, b, g_xy, g_zero, n, out_lr_xy, out_lr_zero, out_ip);
+  }
+  return -1;
+}
+int ref_ipa_fold(int cid, const uint64_t* a, const uint64_t* b, const uint64_t* g_xy, const uint8_t* g_zero, size_t n,
+                 const uint64_t* u, const uint64_t* u_inv, uint64_t* out_a, uint64_t* out_b, uint64_t* out_g_xy, uint8_t* out_g_zero) {
+  if (n < 2 || (n & (n - 1))) return -2;
+  switch (cid) {
+    case 0: return ipa_fold_t<Tweedledee>(a, b, g_xy, g_zero, n, u, u_inv, out_a, out_b, out_g_xy, out_g_zero);
+    case 1: return ipa_fold_t<Tweedledum>(a, b, g_xy, g_zero, n, u, u_inv, out_a, out_b, out_g_xy, out_g_zero);
+    case 2: return ipa_fold_t<Bls12377>(a, b, g_xy, g_zero, n, u, u_inv, out_a, out_b, out_g_xy, out_g_zero);
+  }
+  return -1;
+}
+}  // extern "C"

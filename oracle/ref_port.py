@@ -55,6 +55,8 @@ def lib(native: bool = False):
     L.ref_gen_points.argtypes = [C.c_int, C.c_uint64, C.c_size_t, u64p]
     L.ref_to_digits.argtypes = [C.c_int, u64p, C.c_int, u32p]
     L.ref_set_threads.argtypes = [C.c_int]
+    L.ref_ipa_round_lr.argtypes = [C.c_int, u64p, u64p, u64p, u8p, C.c_size_t, u64p, u8p, u64p]
+    L.ref_ipa_fold.argtypes = [C.c_int, u64p, u64p, u64p, u8p, C.c_size_t, u64p, u64p, u64p, u64p, u64p, u8p]
     if not native:
         _LIB = L
     return L
@@ -201,3 +203,36 @@ def to_digits(cid: int, scalar, w: int):
     out = np.zeros(512, dtype=np.uint32)
     nd = lib().ref_to_digits(cid, _p64(s), w, out.ctypes.data_as(C.POINTER(C.c_uint32)))
     return [int(v) for v in out[:nd]]
+
+
+def ipa_round_lr(cid: int, a, b, g_xy, g_zero=None):
+    """halo.rs:87-93 without blinding / U' terms: ((l_xy, l_zero), (r_xy, r_zero), ip_l, ip_r)."""
+    nl = FIELD_LIMBS[CURVE_BASE[cid]]
+    a, b, g = _arr(a), _arr(b), _arr(g_xy).reshape(-1, 2, nl)
+    n = a.shape[0]
+    z = np.ascontiguousarray(g_zero if g_zero is not None else np.zeros(n, dtype=np.uint8), dtype=np.uint8)
+    lr = np.empty((2, 2, nl), dtype=np.uint64)
+    lrz = np.zeros(2, dtype=np.uint8)
+    ip = np.empty((2, 4), dtype=np.uint64)
+    rc = lib().ref_ipa_round_lr(cid, _p64(a), _p64(b), _p64(g), _p8(z), n, _p64(lr), _p8(lrz), _p64(ip))
+    if rc == -2:
+        raise AssertionError("Not a power of two")
+    assert rc == 0
+    return (lr[0], bool(lrz[0])), (lr[1], bool(lrz[1])), ip[0], ip[1]
+
+
+def ipa_fold(cid: int, a, b, g_xy, g_zero, u, u_inv):
+    """halo.rs:117-123: returns (a', b', g'_xy, g'_zero) of half the length."""
+    nl = FIELD_LIMBS[CURVE_BASE[cid]]
+    a, b, g = _arr(a), _arr(b), _arr(g_xy).reshape(-1, 2, nl)
+    n = a.shape[0]
+    z = np.ascontiguousarray(g_zero if g_zero is not None else np.zeros(n, dtype=np.uint8), dtype=np.uint8)
+    oa, ob = np.empty((n // 2, 4), dtype=np.uint64), np.empty((n // 2, 4), dtype=np.uint64)
+    og = np.empty((n // 2, 2, nl), dtype=np.uint64)
+    oz = np.zeros(n // 2, dtype=np.uint8)
+    rc = lib().ref_ipa_fold(cid, _p64(a), _p64(b), _p64(g), _p8(z), n, _p64(_arr(u)), _p64(_arr(u_inv)), _p64(oa), _p64(ob),
+                            _p64(og), _p8(oz))
+    if rc == -2:
+        raise AssertionError("Not a power of two")
+    assert rc == 0
+    return oa, ob, og, oz

@@ -34,6 +34,7 @@ __all__ = [
     "FftPrecomputation", "fft_precompute", "fft", "fft_with_precomputation", "fft_with_precomputation_power_of_2",
     "ifft_with_precomputation_power_of_2", "fft_batch", "coset_lde", "coset_ifft", "divide_by_z_h",
     "field_op", "batch_multiplicative_inverse", "batch_to_affine", "affine_summation_best", "affine_multisummation_best", "curve_mul", "points_generate", "kernel_launch_count",
+    "HaloIpaRounds",
 ]
 
 # ids of include/plonky_b200.h
@@ -131,6 +132,14 @@ def lib():
     L.plk_curve_mul.argtypes = [C.c_int, u64p, u8p, u64p, sz, u64p, u8p]
     L.plk_points_generate_dev.argtypes = [C.c_int, C.c_uint64, sz, vp, vp]
     L.plk_points_generate.argtypes = [C.c_int, C.c_uint64, sz, u64p]
+    L.plk_ipa_new.argtypes = [C.c_int, u64p, u64p, u64p, u8p, sz, C.POINTER(vp)]
+    L.plk_ipa_len.argtypes = [vp]
+    L.plk_ipa_len.restype = sz
+    L.plk_ipa_free.argtypes = [vp]
+    L.plk_ipa_free.restype = None
+    L.plk_ipa_round_lr.argtypes = [vp, u64p, u8p, u64p, u8p, u64p, u64p]
+    L.plk_ipa_fold.argtypes = [vp, u64p, u64p]
+    L.plk_ipa_read.argtypes = [vp, u64p, u64p, u64p, u8p]
     L.plk_kernel_launch_count.restype = C.c_uint64
     L.plk_set_profiling.argtypes = [C.c_int]
     L.plk_msm_last_phase_ms.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
@@ -484,3 +493,62 @@ def points_generate(curve: int, seed: int, n: int) -> np.ndarray:
     out = np.zeros((n, 2, Lb), dtype=np.uint64)
     _check(lib().plk_points_generate(curve, seed, n, _p64(out)))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Halo inner-product-argument rounds (src/halo.rs:63-124)
+# ------------------------------------------------------------------------------------------------
+class HaloIpaRounds:
+    """halo_a, halo_b, halo_g of batch_opening_proof (halo.rs:53-57) kept on the device for all rounds.
+
+    round_lr()        -> halo.rs:87-93 without the blinding / U' terms (the caller adds [l_j] H + [<a,b>] U')
+    fold(u, u_inv)    -> halo.rs:117-123
+    read()            -> current (a, b, g_xy, g_zero); after the last fold halo_a[0], halo_b[0], halo_g[0].to_affine()
+    """
+
+    def __init__(self, curve: int, a, b, g_xy, g_zero=None):
+        Lb = FIELD_LIMBS[CURVE_BASE_FIELD[curve]]
+        a, b = _u64(a).reshape(-1, 4), _u64(b).reshape(-1, 4)
+        g = _u64(g_xy).reshape(-1, 2, Lb)
+        n = a.shape[0]
+        if b.shape[0] != n or g.shape[0] != n:
+            raise PlonkyPanic("halo_a / halo_b / halo_g length mismatch")        # debug_assert_eq!, halo.rs:67-69
+        z = _zero_flags(g_zero, n)
+        self.curve, self.Lb = curve, Lb
+        self.handle = C.c_void_p()
+        _check(lib().plk_ipa_new(curve, _p64(a), _p64(b), _p64(g), _p8(z), n, C.byref(self.handle)))
+
+    def __len__(self):
+        return int(lib().plk_ipa_len(self.handle))
+
+    def round_lr(self):
+        """((l_xyz, l_zero), (r_xyz, r_zero), ip_l, ip_r)"""
+        l = np.zeros((3, self.Lb), dtype=np.uint64)
+        r = np.zeros((3, self.Lb), dtype=np.uint64)
+        lz, rz = np.zeros(1, dtype=np.uint8), np.zeros(1, dtype=np.uint8)
+        ipl, ipr = np.zeros(4, dtype=np.uint64), np.zeros(4, dtype=np.uint64)
+        _check(lib().plk_ipa_round_lr(self.handle, _p64(l), _p8(lz), _p64(r), _p8(rz), _p64(ipl), _p64(ipr)))
+        return (l, bool(lz[0])), (r, bool(rz[0])), ipl, ipr
+
+    def fold(self, u, u_inv):
+        u, u_inv = _u64(u).reshape(4), _u64(u_inv).reshape(4)
+        _check(lib().plk_ipa_fold(self.handle, _p64(u), _p64(u_inv)))
+
+    def read(self):
+        n = len(self)
+        a, b = np.zeros((n, 4), dtype=np.uint64), np.zeros((n, 4), dtype=np.uint64)
+        g = np.zeros((n, 2, self.Lb), dtype=np.uint64)
+        z = np.zeros(n, dtype=np.uint8)
+        _check(lib().plk_ipa_read(self.handle, _p64(a), _p64(b), _p64(g), _p8(z)))
+        return a, b, g, z
+
+    def close(self):
+        if self.handle:
+            lib().plk_ipa_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

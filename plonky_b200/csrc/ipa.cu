@@ -1,0 +1,149 @@
+// C ABI of the device-resident Halo IPA rounds (include/plonky_b200.h, section "Halo inner-product argument").
+#include <memory>
+#include "ipa_kernels.cuh"
+#include "msm_plan.h"
+
+using namespace plk;
+
+namespace plk {
+const IpaOps* ipa_ops_tweedledee();
+const IpaOps* ipa_ops_tweedledum();
+const IpaOps* ipa_ops_bls12_377();
+}
+
+struct plk_ipa_state {
+  int curve = 0;
+  size_t n = 0;            // current length of halo_a / halo_b / halo_g (halves every fold)
+  size_t L = 4;            // u64 limbs of a base-field element
+  DevBuf a, b, g;          // n scalars (32 B), n scalars, n affine points (2 * L * 8 B, identity = (0, 0))
+  DevBuf partials, io;     // inner-product partials; io: 2 points xyz | 2 flags (8 B each) | 2 inner products | u, u^-1
+};
+
+namespace {
+const IpaOps* ipa_ops_for(int curve) {
+  switch (curve) {
+    case PLK_CURVE_TWEEDLEDEE: return ipa_ops_tweedledee();
+    case PLK_CURVE_TWEEDLEDUM: return ipa_ops_tweedledum();
+    case PLK_CURVE_BLS12_377: return ipa_ops_bls12_377();
+  }
+  fail(PLK_EINVAL, "unknown curve id");
+}
+// identity points arrive as zero flags: force their coordinates to (0, 0), the device encoding
+__global__ void ipa_apply_zero_flags(uint4* g, const unsigned char* zero, unsigned long long n, unsigned vec_per_point) {
+  const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (i >= n || !zero[i]) return;
+  for (unsigned k = 0; k < vec_per_point; ++k) g[i * vec_per_point + k] = make_uint4(0, 0, 0, 0);
+}
+__global__ void ipa_zero_flags_of(const uint4* g, unsigned char* zero, unsigned long long n, unsigned vec_per_point) {
+  const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned acc = 0;
+  for (unsigned k = 0; k < vec_per_point; ++k) { const uint4 v = g[i * vec_per_point + k]; acc |= v.x | v.y | v.z | v.w; }
+  zero[i] = acc == 0 ? 1 : 0;
+}
+}  // namespace
+
+extern "C" {
+
+int plk_ipa_new(int curve, const uint64_t* a, const uint64_t* b, const uint64_t* g_xy, const uint8_t* g_zero, size_t n,
+                plk_ipa_state** out) {
+  return guarded([&] {
+    if (!out) fail(PLK_EINVAL, "NULL out");
+    *out = nullptr;
+    const int bf = plk_curve_base_field(curve);
+    if (bf < 0) fail(PLK_EINVAL, "unknown curve id");
+    if (!is_pow2(n)) fail(PLK_ENOTPOW2, "Not a power of two");            // log2_strict(degree), halo.rs:62
+    if (!a || !b || !g_xy) fail(PLK_EINVAL, "NULL buffer");
+    std::unique_ptr<plk_ipa_state> s(new plk_ipa_state());
+    s->curve = curve;
+    s->n = n;
+    s->L = (size_t)plk_field_limbs(bf);
+    cudaStream_t st = thread_stream();
+    const size_t pb = 2 * s->L * 8;
+    s->a.alloc(n * 32);
+    s->b.alloc(n * 32);
+    s->g.alloc(n * pb);
+    s->partials.alloc(2 * kIpaMaxBlocks * 32);
+    s->io.alloc(1024);
+    PLK_CUDA(cudaMemcpyAsync(s->a.p, a, n * 32, cudaMemcpyHostToDevice, st));
+    PLK_CUDA(cudaMemcpyAsync(s->b.p, b, n * 32, cudaMemcpyHostToDevice, st));
+    PLK_CUDA(cudaMemcpyAsync(s->g.p, g_xy, n * pb, cudaMemcpyHostToDevice, st));
+    if (g_zero) {
+      DevBuf dz(n, st);
+      PLK_CUDA(cudaMemcpyAsync(dz.p, g_zero, n, cudaMemcpyHostToDevice, st));
+      ipa_apply_zero_flags<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->g.as<uint4>(), dz.as<unsigned char>(), n, (unsigned)(pb / 16));
+      PLK_LAUNCHED();
+    }
+    PLK_CUDA(cudaStreamSynchronize(st));
+    *out = s.release();
+  });
+}
+size_t plk_ipa_len(const plk_ipa_state* s) { return s ? s->n : 0; }
+void plk_ipa_free(plk_ipa_state* s) { delete s; }
+
+int plk_ipa_round_lr(plk_ipa_state* s, uint64_t* out_l_xyz, uint8_t* out_l_zero, uint64_t* out_r_xyz, uint8_t* out_r_zero,
+                     uint64_t* out_ip_l, uint64_t* out_ip_r) {
+  return guarded([&] {
+    if (!s) fail(PLK_EINVAL, "NULL state");
+    if (!out_l_xyz || !out_l_zero || !out_r_xyz || !out_r_zero || !out_ip_l || !out_ip_r) fail(PLK_EINVAL, "NULL buffer");
+    if (s->n < 2) fail(PLK_EINVAL, "no round left: the vectors have length 1");
+    cudaStream_t st = thread_stream();
+    const size_t half = s->n / 2, pb = 2 * s->L * 8, xyz = 3 * s->L * 8;
+    char* io = s->io.as<char>();
+    char* d_l = io;
+    char* d_r = io + xyz;
+    char* d_flags = io + 2 * xyz;             // 2 x 8 bytes
+    char* d_ip = io + 2 * xyz + 16;           // 2 x 32 bytes
+    const char* a = s->a.as<char>();
+    const char* g = s->g.as<char>();
+    msm_variable_dev(s->curve, g + half * pb, a, half, d_l, d_flags, st);              // <a_lo, G_hi>  (halo.rs:87)
+    msm_variable_dev(s->curve, g, a + half * 32, half, d_r, d_flags + 8, st);          // <a_hi, G_lo>  (halo.rs:91)
+    ipa_ops_for(s->curve)->inner_products(s->a.p, s->b.p, half, s->partials.p, d_ip, st);
+    uint8_t flags[16];
+    PLK_CUDA(cudaMemcpyAsync(out_l_xyz, d_l, xyz, cudaMemcpyDeviceToHost, st));
+    PLK_CUDA(cudaMemcpyAsync(out_r_xyz, d_r, xyz, cudaMemcpyDeviceToHost, st));
+    PLK_CUDA(cudaMemcpyAsync(flags, d_flags, 16, cudaMemcpyDeviceToHost, st));
+    PLK_CUDA(cudaMemcpyAsync(out_ip_l, d_ip, 32, cudaMemcpyDeviceToHost, st));
+    PLK_CUDA(cudaMemcpyAsync(out_ip_r, d_ip + 32, 32, cudaMemcpyDeviceToHost, st));
+    PLK_CUDA(cudaStreamSynchronize(st));
+    *out_l_zero = flags[0];
+    *out_r_zero = flags[8];
+  });
+}
+
+int plk_ipa_fold(plk_ipa_state* s, const uint64_t* u, const uint64_t* u_inv) {
+  return guarded([&] {
+    if (!s || !u || !u_inv) fail(PLK_EINVAL, "NULL argument");
+    if (s->n < 2) fail(PLK_EINVAL, "no round left: the vectors have length 1");
+    cudaStream_t st = thread_stream();
+    const size_t half = s->n / 2;
+    char* d_uu = s->io.as<char>() + 512;
+    PLK_CUDA(cudaMemcpyAsync(d_uu, u, 32, cudaMemcpyHostToDevice, st));
+    PLK_CUDA(cudaMemcpyAsync(d_uu + 32, u_inv, 32, cudaMemcpyHostToDevice, st));
+    ipa_ops_for(s->curve)->fold(s->a.p, s->b.p, s->g.p, half, d_uu, st);
+    PLK_CUDA(cudaStreamSynchronize(st));     // u / u_inv are the caller's stack memory
+    s->n = half;
+  });
+}
+
+int plk_ipa_read(const plk_ipa_state* s, uint64_t* a, uint64_t* b, uint64_t* g_xy, uint8_t* g_zero) {
+  return guarded([&] {
+    if (!s) fail(PLK_EINVAL, "NULL state");
+    cudaStream_t st = thread_stream();
+    const size_t pb = 2 * s->L * 8;
+    if (a) PLK_CUDA(cudaMemcpyAsync(a, s->a.p, s->n * 32, cudaMemcpyDeviceToHost, st));
+    if (b) PLK_CUDA(cudaMemcpyAsync(b, s->b.p, s->n * 32, cudaMemcpyDeviceToHost, st));
+    if (g_xy) PLK_CUDA(cudaMemcpyAsync(g_xy, s->g.p, s->n * pb, cudaMemcpyDeviceToHost, st));
+    if (g_zero) {
+      DevBuf dz(s->n, st);
+      ipa_zero_flags_of<<<(unsigned)((s->n + 255) / 256), 256, 0, st>>>(s->g.as<uint4>(), dz.as<unsigned char>(), s->n, (unsigned)(pb / 16));
+      PLK_LAUNCHED();
+      PLK_CUDA(cudaMemcpyAsync(g_zero, dz.p, s->n, cudaMemcpyDeviceToHost, st));
+      PLK_CUDA(cudaStreamSynchronize(st));
+      return;
+    }
+    PLK_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+}  // extern "C"

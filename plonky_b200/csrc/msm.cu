@@ -70,7 +70,8 @@ plk_msm_scratch* scratch_for(plk_msm_table* t, cudaStream_t st) {
     const size_t xyzz = 2 * t->point_bytes;
     auto* s = new plk_msm_scratch();
     if (t->temporary)
-      for (plk::DevBuf* b : {&s->counts, &s->offsets, &s->task_off, &s->cursors, &s->sorted, &s->partials, &s->buckets, &s->ranges, &s->big_list})
+      for (plk::DevBuf* b : {&s->counts, &s->offsets, &s->task_off, &s->cursors, &s->sorted, &s->partials, &s->buckets, &s->ranges, &s->big_list,
+                             &s->cta_hist})
         b->set_async(st);
     try {
       s->counts.alloc((size_t)g.nb * 4);
@@ -82,6 +83,18 @@ plk_msm_scratch* scratch_for(plk_msm_table* t, cudaStream_t st) {
       s->buckets.alloc((size_t)g.nb * xyzz);
       s->ranges.alloc(((size_t)g.nb / kRangeSize + 1) * xyzz);
       s->big_list.alloc(((size_t)g.nb + 1) * 4);
+      // fixed-base geometry whose histogram fits in shared memory: per-CTA histograms instead of global atomics
+      static const bool smem_sort = !(getenv("PLK_MSM_SORT") && atoi(getenv("PLK_MSM_SORT")) == 0);
+      if (smem_sort && !g.variable && g.nb <= kSortMaxBins && g.n >= 4096) {
+        int dev = 0, sms = 0;
+        PLK_CUDA(cudaGetDevice(&dev));
+        PLK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        size_t rows = g.n / 2048;
+        if (rows > (size_t)sms) rows = sms;
+        if (rows < 1) rows = 1;
+        s->sort_rows = (unsigned)rows;
+        s->cta_hist.alloc(rows * g.nb * 4);
+      }
     } catch (...) {
       delete s;
       throw;
@@ -200,6 +213,26 @@ void execute_host(plk_msm_table* t, const uint64_t* scalars, size_t n, size_t k,
 }
 
 }  // namespace
+
+namespace plk {
+void msm_variable_dev(int curve, const void* d_points_xy, const void* d_scalars, size_t n, void* d_out_xyz, void* d_out_zero,
+                      cudaStream_t st) {
+  plk_msm_table* t = new_table(curve, n, 8, true);
+  try {
+    t->temporary = true;
+    t->temp_stream = st;
+    t->table.set_async(st);
+    t->point_bytes = 2 * curve_base_limbs64(curve) * 8;
+    ops_for(curve)->table_build(t, d_points_xy, st);
+    alloc_scratch(t);
+    run_one(t, d_scalars, d_out_xyz, d_out_zero, nullptr, st);
+  } catch (...) {
+    delete t;
+    throw;
+  }
+  delete t;      // stream-ordered frees: the buffers outlive the kernels queued above
+}
+}  // namespace plk
 
 extern "C" {
 

@@ -123,6 +123,70 @@ __global__ void msm_scatter_kernel(const uint4* __restrict__ scalars, MsmGeom g,
   });
 }
 
+// ---- counting sort without global atomics (fixed-base geometry, nb * 4 B fits in shared memory) ----
+// The L2 atomic unit serves ~1e11 atomics/s: 2 x 16.7 M global atomics were 0.45 ms of a 3.7 ms execute.  Here CTA k
+// owns the scalars [k * chunk, (k + 1) * chunk): msm_hist_kernel histograms its digits in shared memory and stores the
+// row cta_hist[k][.]; msm_colsum_kernel turns each column into exclusive prefixes over the CTAs (+ the bucket totals);
+// after the scan msm_scatter_smem_kernel re-derives the same digits and takes positions from shared-memory cursors
+// initialised to offsets[b] + cta_hist[k][b].  Entries of one bucket end up grouped by CTA; their order inside a
+// group depends on the atomics' arrival order, which only permutes the terms of a sum.
+template <class C>
+__global__ void __launch_bounds__(1024) msm_hist_kernel(const uint4* __restrict__ scalars, MsmGeom g, unsigned chunk,
+                                                        unsigned* __restrict__ cta_hist) {
+  typedef Fp<typename C::Scalar> SF;
+  extern __shared__ unsigned sh_bins[];
+  for (unsigned b = threadIdx.x; b < g.nb; b += blockDim.x) sh_bins[b] = 0;
+  __syncthreads();
+  const unsigned long long lo = (unsigned long long)blockIdx.x * chunk;
+  unsigned long long hi = lo + chunk;
+  if (hi > g.n) hi = g.n;
+  for (unsigned long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    SF s = SF::to_canonical(load_fp<SF>(scalars, i));     // curve_msm.rs:164 to_canonical_u64_vec
+    for_each_digit(s, g, [&](int, unsigned b, bool) { atomicAdd(&sh_bins[b], 1u); });
+  }
+  __syncthreads();
+  unsigned* row = cta_hist + (size_t)blockIdx.x * g.nb;
+  for (unsigned b = threadIdx.x; b < g.nb; b += blockDim.x) row[b] = sh_bins[b];
+}
+// one thread per bucket: cta_hist[k][b] <- sum_{k' < k} cta_hist[k'][b], counts[b] <- column total
+static __global__ void msm_colsum_kernel(unsigned* __restrict__ cta_hist, unsigned nb, unsigned rows, unsigned* __restrict__ counts) {
+  const unsigned b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  unsigned run = 0;
+  // batches of 16 rows: the loads of a batch are independent (a load-store-load chain over `rows` L2 round trips was 90 us)
+  for (unsigned k0 = 0; k0 < rows; k0 += 16) {
+    unsigned v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = (k0 + u < rows) ? cta_hist[(size_t)(k0 + u) * nb + b] : 0u;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      if (k0 + u < rows) cta_hist[(size_t)(k0 + u) * nb + b] = run;
+      run += v[u];
+    }
+  }
+  counts[b] = run;
+}
+template <class C>
+__global__ void __launch_bounds__(1024) msm_scatter_smem_kernel(const uint4* __restrict__ scalars, MsmGeom g, unsigned chunk,
+                                                                const unsigned* __restrict__ cta_hist, const unsigned* __restrict__ offsets,
+                                                                unsigned* __restrict__ sorted) {
+  typedef Fp<typename C::Scalar> SF;
+  extern __shared__ unsigned sh_bins[];
+  const unsigned* row = cta_hist + (size_t)blockIdx.x * g.nb;
+  for (unsigned b = threadIdx.x; b < g.nb; b += blockDim.x) sh_bins[b] = offsets[b] + row[b];
+  __syncthreads();
+  const unsigned long long lo = (unsigned long long)blockIdx.x * chunk;
+  unsigned long long hi = lo + chunk;
+  if (hi > g.n) hi = g.n;
+  for (unsigned long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    SF s = SF::to_canonical(load_fp<SF>(scalars, i));
+    for_each_digit(s, g, [&](int j, unsigned b, bool negative) {
+      const unsigned pos = atomicAdd(&sh_bins[b], 1u);
+      sorted[pos] = (unsigned)((unsigned long long)j * g.n + i) | (negative ? 0x80000000u : 0u);
+    });
+  }
+}
+
 template <class C>
 __device__ __forceinline__ Affine<C> load_affine(const void* table, size_t slot) {
   typedef Fp<typename C::Base> F;
@@ -197,6 +261,8 @@ __global__ void msm_bucket_sum_kernel(const void* __restrict__ partials, const u
     big_list[1 + atomicAdd(&big_list[0], 1u)] = b;
     return;
   }
+  // (four lanes per bucket with a shuffle butterfly was measured slower: 0.27 vs 0.22 ms -- the tails pay per warp
+  // instruction, not per active lane)
   XYZZ<C> acc = XYZZ<C>::identity();
   for (unsigned t = t0; t < t1; ++t) acc = XYZZ<C>::add(acc, load_xyzz<C>(partials, t));
   store_xyzz<C>(buckets, b, acc);
@@ -548,21 +614,46 @@ void execute_one(plk_msm_table* t, plk_msm_scratch* s, const void* d_scalars, vo
     }
     return;
   }
-  PLK_CUDA(cudaMemsetAsync(s->counts.p, 0, (size_t)g.nb * 4, st));
   PLK_CUDA(cudaMemsetAsync(s->big_list.p, 0, 4, st));
   s->timer.begin(st);
-  const unsigned sblocks = (unsigned)((g.n + 255) / 256);
-  msm_count_kernel<C><<<sblocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(d_scalars), g, s->counts.as<unsigned>());
-  PLK_LAUNCHED();
-  s->timer.mark(st);
-  msm_scan_kernel<<<1, 1024, 0, st>>>(s->counts.as<unsigned>(), g.nb, g.task, s->offsets.as<unsigned>(), s->task_off.as<unsigned>(),
-                                      s->cursors.as<unsigned>());
-  PLK_LAUNCHED();
-  s->timer.mark(st);
-  msm_scatter_kernel<C><<<sblocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(d_scalars), g, s->cursors.as<unsigned>(),
-                                                 s->sorted.as<unsigned>());
-  PLK_LAUNCHED();
-  s->timer.mark(st);
+  if (s->sort_rows) {
+    // shared-memory histograms per CTA, no global atomics (see msm_hist_kernel)
+    const unsigned rows = s->sort_rows, chunk = (unsigned)((g.n + rows - 1) / rows);
+    const size_t smem = (size_t)g.nb * 4;
+    static bool attr_done = false;
+    if (!attr_done) {
+      PLK_CUDA(cudaFuncSetAttribute(msm_hist_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortMaxBins * 4));
+      PLK_CUDA(cudaFuncSetAttribute(msm_scatter_smem_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortMaxBins * 4));
+      attr_done = true;
+    }
+    msm_hist_kernel<C><<<rows, 1024, smem, st>>>(reinterpret_cast<const uint4*>(d_scalars), g, chunk, s->cta_hist.as<unsigned>());
+    PLK_LAUNCHED();
+    msm_colsum_kernel<<<(g.nb + 255) / 256, 256, 0, st>>>(s->cta_hist.as<unsigned>(), g.nb, rows, s->counts.as<unsigned>());
+    PLK_LAUNCHED();
+    s->timer.mark(st);
+    msm_scan_kernel<<<1, 1024, 0, st>>>(s->counts.as<unsigned>(), g.nb, g.task, s->offsets.as<unsigned>(), s->task_off.as<unsigned>(),
+                                        s->cursors.as<unsigned>());
+    PLK_LAUNCHED();
+    s->timer.mark(st);
+    msm_scatter_smem_kernel<C><<<rows, 1024, smem, st>>>(reinterpret_cast<const uint4*>(d_scalars), g, chunk, s->cta_hist.as<unsigned>(),
+                                                         s->offsets.as<unsigned>(), s->sorted.as<unsigned>());
+    PLK_LAUNCHED();
+    s->timer.mark(st);
+  } else {
+    PLK_CUDA(cudaMemsetAsync(s->counts.p, 0, (size_t)g.nb * 4, st));
+    const unsigned sblocks = (unsigned)((g.n + 255) / 256);
+    msm_count_kernel<C><<<sblocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(d_scalars), g, s->counts.as<unsigned>());
+    PLK_LAUNCHED();
+    s->timer.mark(st);
+    msm_scan_kernel<<<1, 1024, 0, st>>>(s->counts.as<unsigned>(), g.nb, g.task, s->offsets.as<unsigned>(), s->task_off.as<unsigned>(),
+                                        s->cursors.as<unsigned>());
+    PLK_LAUNCHED();
+    s->timer.mark(st);
+    msm_scatter_kernel<C><<<sblocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(d_scalars), g, s->cursors.as<unsigned>(),
+                                                   s->sorted.as<unsigned>());
+    PLK_LAUNCHED();
+    s->timer.mark(st);
+  }
   const unsigned ablocks = (unsigned)((t->max_tasks + kAccThreads - 1) / kAccThreads);
   msm_accumulate_kernel<C><<<ablocks, kAccThreads, 0, st>>>(t->table.p, s->sorted.as<unsigned>(), s->offsets.as<unsigned>(),
                                                             s->task_off.as<unsigned>(), g.nb, g.task, s->partials.p);

@@ -5,10 +5,11 @@
 #include "common.cuh"
 
 namespace plk {
-constexpr int kTaskSizeMax = 64;     // S: additions per accumulate task (smaller for small MSMs: more threads)
+constexpr int kTaskSizeMax = 32;     // S: additions per accumulate task (smaller for small MSMs: more threads)
 constexpr int kBigBucket = 32;       // buckets with more task partials than this are summed by a whole CTA
 constexpr int kRangeSize = 8;        // buckets per running-sum range
 constexpr int kAccThreads = 128;
+constexpr unsigned kSortMaxBins = 32768;   // shared-memory histogram sort: nb * 4 B <= 128 KiB
 
 struct MsmGeom {
   unsigned long long n;     // terms
@@ -27,6 +28,8 @@ struct MsmGeom {
 // internal streams; independent host threads use their own) never share buffers.
 struct plk_msm_scratch {
   plk::DevBuf counts, offsets, task_off, cursors, sorted, partials, buckets, ranges, big_list;   // big_list[0] = count
+  plk::DevBuf cta_hist;    // sort_rows x nb per-CTA histograms / column prefixes (shared-memory sort)
+  unsigned sort_rows = 0;  // CTAs of the shared-memory sort; 0 = global-atomic counting sort
   plk::PhaseTimer timer;   // count | scan | scatter | accumulate | bucket_sum | range | final
 };
 
@@ -69,4 +72,8 @@ struct MsmOps {
                    unsigned char* d_out_zero, cudaStream_t st);
   void (*curve_mul)(const void* d_points_xy, const void* d_scalars, size_t n, void* d_out_xyz, unsigned char* d_out_zero, cudaStream_t st);
 };
+// msm_parallel on device buffers (variable base, no table of powers; src/curve/curve_msm.rs:54-61): n affine points
+// (identity = (0, 0)) and n Montgomery scalars -> one normalised point (3*L u64) + zero flag, asynchronous on `st`.
+void msm_variable_dev(int curve, const void* d_points_xy, const void* d_scalars, size_t n, void* d_out_xyz, void* d_out_zero,
+                      cudaStream_t st);
 }  // namespace plk
