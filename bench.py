@@ -245,7 +245,11 @@ def run_ours(args):
         n //= world
 
     # ---- setup (untimed): synthetic generators on device, fixed-base table, scalar buffers ----
-    pts = pkd.points_generate_dev(curve, SEED + 1 + rank * n, n)
+    if args.generators == "reference":
+        # rank r owns pedersen_g[r n .. (r + 1) n) = blake_hash_usize_to_curve(i) (circuit_builder.rs:1127), derived on device
+        pts = pkd.pedersen_generators_dev(curve, rank * n, n)
+    else:
+        pts = pkd.points_generate_dev(curve, SEED + 1 + rank * n, n)
     torch.cuda.synchronize()
     t_pre = time.perf_counter()
     table = pkd.msm_precompute_affine_dev(curve, pts, 11)        # synchronous: the msm_precompute of the reference
@@ -338,7 +342,7 @@ def run_ours(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if args.total_terms else "weak", "vs_baseline": None,
         "dtype": "u64x6 (Montgomery, 377-bit base field)" if curve == 2 else "u64x4 (Montgomery, 255-bit)", "data": "synthetic",
         "config": {"workload": f"{curve_name} G1 MSM, {n} terms per GPU, fixed-base table (msm_precompute once, execute timed)",
-                   "terms_per_gpu": n, "total_terms": world * n, "window_passed": 11, "precompute_ms_untimed": precompute_ms,
+                   "terms_per_gpu": n, "total_terms": world * n, "window_passed": 11, "generators": ("pedersen_g = blake_hash_usize_to_curve(i), derived on device (hash_to_curve.rs:53-76)" if args.generators == "reference" else "synthetic [k_i] G"), "precompute_ms_untimed": precompute_ms,
                    "l2": "inputs larger than L2: the table walk per step (16 windows x terms x point size) + 4 rotating scalar vectors",
                    "multi_gpu": "shard per rank, all-gather of 128 B partials, combine on every rank" if world > 1 else "single GPU"},
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": None,
@@ -470,6 +474,8 @@ def main():
     ap.add_argument("--curve", default="tweedledee", choices=["tweedledee", "tweedledum", "bls12_377"],
                     help="MSM curve (BASELINE config 4 uses bls12_377 with --msm-log-n 22 on 8 GPUs: 2^22 terms in total)")
     ap.add_argument("--total-terms", action="store_true", help="--msm-log-n is the TOTAL across ranks (strong scaling, config 4)")
+    ap.add_argument("--generators", default="reference", choices=["reference", "synthetic"],
+                    help="reference: pedersen_g = blake_hash_usize_to_curve(i) as in circuit_builder.rs:1127; synthetic: [k_i] G")
     ap.add_argument("--skip-ntt", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()

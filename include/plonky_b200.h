@@ -226,6 +226,14 @@ typedef struct plk_ipa_state plk_ipa_state;
  * of two (PLK_ENOTPOW2 = log2_strict(degree), halo.rs:62). */
 int plk_ipa_new(int curve, const uint64_t* a, const uint64_t* b, const uint64_t* g_xy, const uint8_t* g_zero,
                 size_t n, plk_ipa_state** out);
+/* Same rounds against the fixed-base table of the n generators (the prover already holds
+ * pedersen_g_msm_precomputation, src/plonk.rs:64-69): G is never folded.  The folded generators are kept as
+ * coefficients c_i over the original ones, L_j / R_j become two fixed-base MSMs per round and halo_g one MSM of the
+ * c_i at the end -- the same group elements as halo.rs:87-123 without 255 doublings per generator and round.
+ * The table is borrowed and must outlive the state; n must equal its length (PLK_ELENGTH).  plk_ipa_read returns
+ * g only once the length is 1. */
+int plk_ipa_new_with_table(const plk_msm_table* table, const uint64_t* a, const uint64_t* b, size_t n,
+                           plk_ipa_state** out);
 size_t plk_ipa_len(const plk_ipa_state* s);     /* current vector length (halves with every fold) */
 void plk_ipa_free(plk_ipa_state* s);
 /* First half of a round (halo.rs:87-93): out_l = msm_parallel(a_lo, G_hi, 8), out_r = msm_parallel(a_hi, G_lo, 8)
@@ -239,6 +247,29 @@ int plk_ipa_fold(plk_ipa_state* s, const uint64_t* u, const uint64_t* u_inv);
 /* Copy the current vectors out (any pointer may be NULL): after the last fold these are halo_a[0], halo_b[0]
  * and halo_g[0].to_affine() (halo.rs:126-131).  g_xy: len*2*L limbs, g_zero: len bytes. */
 int plk_ipa_read(const plk_ipa_state* s, uint64_t* a, uint64_t* b, uint64_t* g_xy, uint8_t* g_zero);
+
+/* ------------------------------------------------------------------------------------------
+ * Generator derivation and the point wire format  (src/hash_to_curve.rs, src/serialization.rs)
+ * ---------------------------------------------------------------------------------------- */
+/* blake_hash_usize_to_curve(seed) for seed = seed_start .. seed_start + n - 1 (src/hash_to_curve.rs:53-76): the
+ * derivation of pedersen_g (seeds 0..degree), pedersen_h (degree) and U (degree + 1) in CircuitBuilder::build
+ * (src/circuit_builder.rs:1127-1129) and verify_proof (src/verifier.rs:151-174).  BLAKE3 (the reference's blake3
+ * crate) is implemented on device for the single-block inputs this needs.  Output: n affine points (2*L limbs). */
+int plk_blake_hash_usize_to_curve(int curve, uint64_t seed_start, size_t n, uint64_t* points_xy);
+int plk_blake_hash_usize_to_curve_dev(int curve, uint64_t seed_start, size_t n, void* d_points_xy, void* stream);
+/* blake_hash_base_field_to_curve(seed) for n arbitrary base-field seeds (L limbs each, Montgomery) (:57-76) */
+int plk_blake_hash_base_field_to_curve(int curve, const uint64_t* seeds, size_t n, uint64_t* points_xy);
+/* AffinePoint ToBytes / FromBytes (src/serialization.rs:32-72): per point one mask byte (bit 0: zero, bit 1: y is
+ * odd) followed by x as 8*L canonical little-endian bytes; plk_point_compressed_bytes = 1 + 8*L is the stride.
+ * (The reference's `read` consumes only the mask byte of a zero point although `write` emits 1 + 8*L bytes; the
+ * fixed stride here follows `write`.)  Decompression recomputes y with Field::square_root
+ * (src/field/field.rs:440-473, the reference's Tonelli-Shanks loop, hence the same root).  out_status (optional,
+ * n bytes): 0 ok, 1 "Out of range", 2 "Invalid x coordinate"; any non-zero status makes the call return PLK_EINVAL
+ * (the reference returns io::Error). */
+size_t plk_point_compressed_bytes(int curve);
+int plk_points_compress(int curve, const uint64_t* points_xy, const uint8_t* zero, size_t n, uint8_t* out);
+int plk_points_decompress(int curve, const uint8_t* in, size_t n, uint64_t* out_xy, uint8_t* out_zero,
+                          uint8_t* out_status);
 
 /* number of CUDA kernels this library has launched in the calling process (bench.py: gpu_launches) */
 uint64_t plk_kernel_launch_count(void);

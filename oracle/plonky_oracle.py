@@ -495,6 +495,117 @@ def halo_fold(curve: Curve, a: Sequence[int], b: Sequence[int], g: Sequence[Affi
     return na, nb, ng
 
 
+# ---------------------------------------------------------------------------------------------
+# src/hash_to_curve.rs:13-76 -- BLAKE3-based generator derivation (pedersen_g / pedersen_h / U of
+# src/circuit_builder.rs:1127-1129).  The reference depends on the blake3 crate (Cargo.toml: blake3 = "0.3.3"),
+# absent from /root/reference: this restates the published BLAKE3 compression function for the only case the
+# path needs -- inputs of at most one 64-byte block, at most 64 bytes of extended output -- and is pinned
+# against the independent `blake3` Python package (tests/test_hash_to_curve.py, tools/gen_blake_golden.py).
+# ---------------------------------------------------------------------------------------------
+BLAKE3_IV = (0x6A09E667, 0xBB67AE85, 0x3C6EF372, 0xA54FF53A, 0x510E527F, 0x9B05688C, 0x1F83D9AB, 0x5BE0CD19)
+BLAKE3_MSG_PERMUTATION = (2, 6, 3, 10, 7, 0, 4, 13, 1, 11, 12, 5, 9, 14, 15, 8)
+BLAKE3_CHUNK_START, BLAKE3_CHUNK_END, BLAKE3_ROOT = 1, 2, 8
+
+
+def _rotr32(x: int, n: int) -> int:
+    return ((x >> n) | (x << (32 - n))) & 0xFFFFFFFF
+
+
+def blake3_compress(cv: Sequence[int], block_words: Sequence[int], counter: int, block_len: int, flags: int) -> List[int]:
+    """The BLAKE3 compression function: 7 rounds of the quarter-round G over a 4x4 state, full 16-word output."""
+    v = list(cv) + list(BLAKE3_IV[:4]) + [counter & 0xFFFFFFFF, (counter >> 32) & 0xFFFFFFFF, block_len, flags]
+    m = list(block_words)
+
+    def g(a, b, c, d, mx, my):
+        v[a] = (v[a] + v[b] + mx) & 0xFFFFFFFF
+        v[d] = _rotr32(v[d] ^ v[a], 16)
+        v[c] = (v[c] + v[d]) & 0xFFFFFFFF
+        v[b] = _rotr32(v[b] ^ v[c], 12)
+        v[a] = (v[a] + v[b] + my) & 0xFFFFFFFF
+        v[d] = _rotr32(v[d] ^ v[a], 8)
+        v[c] = (v[c] + v[d]) & 0xFFFFFFFF
+        v[b] = _rotr32(v[b] ^ v[c], 7)
+
+    for rnd in range(7):
+        g(0, 4, 8, 12, m[0], m[1])
+        g(1, 5, 9, 13, m[2], m[3])
+        g(2, 6, 10, 14, m[4], m[5])
+        g(3, 7, 11, 15, m[6], m[7])
+        g(0, 5, 10, 15, m[8], m[9])
+        g(1, 6, 11, 12, m[10], m[11])
+        g(2, 7, 8, 13, m[12], m[13])
+        g(3, 4, 9, 14, m[14], m[15])
+        if rnd < 6:
+            m = [m[BLAKE3_MSG_PERMUTATION[i]] for i in range(16)]
+    for i in range(8):
+        v[i] ^= v[i + 8]
+        v[i + 8] ^= cv[i]
+    return v
+
+
+def blake3_xof_one_block(data: bytes, out_len: int) -> bytes:
+    """blake3::Hasher::new().update(data).finalize_xof().fill(out) for len(data) <= 64 and out_len <= 64."""
+    assert len(data) <= 64 and out_len <= 64
+    block = data + bytes(64 - len(data))
+    words = [int.from_bytes(block[4 * i:4 * i + 4], "little") for i in range(16)]
+    out = blake3_compress(BLAKE3_IV, words, 0, len(data), BLAKE3_CHUNK_START | BLAKE3_CHUNK_END | BLAKE3_ROOT)
+    return b"".join(w.to_bytes(4, "little") for w in out)[:out_len]
+
+
+def blake_field(field: Field, it: int, seed: int) -> Tuple[int, bool]:
+    """blake_field(iter, seed) (hash_to_curve.rs:13-51): (x, y_neg)."""
+    nbytes = 8 * field.limbs
+    j = 0
+    while True:
+        data = seed.to_bytes(nbytes, "little") + bytes([it, j])
+        h = bytearray(blake3_xof_one_block(data, nbytes + 1))
+        h[nbytes - 1] >>= 8 * nbytes - field.bits
+        x = int.from_bytes(h[:nbytes], "little")
+        if x < field.p:                                    # from_canonical_u8_vec: Err("Out of range") otherwise
+            return x, (h[nbytes] & 1) == 1
+        j += 1
+
+
+def blake_hash_base_field_to_curve(curve: Curve, seed: int) -> Affine:
+    """hash_to_curve.rs:57-76 (MapToGroup)."""
+    f = curve.base
+    i = 0
+    while True:
+        x, y_neg = blake_field(f, i, seed)
+        y = f.sqrt((x * x * x + curve.a * x + curve.b) % f.p)      # Field::square_root, field.rs:440-473
+        if y is not None:
+            if y_neg:
+                y = (-y) % f.p
+            return (x, y)
+        i += 1
+
+
+def blake_hash_usize_to_curve(curve: Curve, seed: int) -> Affine:
+    return blake_hash_base_field_to_curve(curve, seed)     # from_canonical_usize(seed), hash_to_curve.rs:53-55
+
+
+# src/serialization.rs:32-72 -- AffinePoint ToBytes / FromBytes
+def point_to_bytes(curve: Curve, P: Affine) -> bytes:
+    nbytes = 8 * curve.base.limbs
+    if P is None:
+        return bytes([1]) + bytes(nbytes)                  # zero = 1, y = ZERO is even, x = ZERO
+    return bytes([(P[1] & 1) << 1]) + P[0].to_bytes(nbytes, "little")
+
+
+def point_from_bytes(curve: Curve, data: bytes) -> Affine:
+    f = curve.base
+    mask = data[0]
+    if mask & 1:
+        return None
+    x = int.from_bytes(data[1:1 + 8 * f.limbs], "little")
+    if x >= f.p:
+        raise ValueError("Out of range")
+    y = f.sqrt((x * x * x + curve.a * x + curve.b) % f.p)
+    if y is None:
+        raise ValueError("Invalid x coordinate")
+    return (x, y) if (y & 1) == ((mask & 2) >> 1) else (x, (-y) % f.p)
+
+
 class SplitMix64:
     def __init__(self, seed: int):
         self.s = seed & MASK64

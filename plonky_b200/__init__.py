@@ -34,7 +34,7 @@ __all__ = [
     "FftPrecomputation", "fft_precompute", "fft", "fft_with_precomputation", "fft_with_precomputation_power_of_2",
     "ifft_with_precomputation_power_of_2", "fft_batch", "coset_lde", "coset_ifft", "divide_by_z_h",
     "field_op", "batch_multiplicative_inverse", "batch_to_affine", "affine_summation_best", "affine_multisummation_best", "curve_mul", "points_generate", "kernel_launch_count",
-    "HaloIpaRounds",
+    "HaloIpaRounds", "blake_hash_usize_to_curve", "blake_hash_base_field_to_curve", "points_to_bytes", "points_from_bytes",
 ]
 
 # ids of include/plonky_b200.h
@@ -133,6 +133,7 @@ def lib():
     L.plk_points_generate_dev.argtypes = [C.c_int, C.c_uint64, sz, vp, vp]
     L.plk_points_generate.argtypes = [C.c_int, C.c_uint64, sz, u64p]
     L.plk_ipa_new.argtypes = [C.c_int, u64p, u64p, u64p, u8p, sz, C.POINTER(vp)]
+    L.plk_ipa_new_with_table.argtypes = [vp, u64p, u64p, sz, C.POINTER(vp)]
     L.plk_ipa_len.argtypes = [vp]
     L.plk_ipa_len.restype = sz
     L.plk_ipa_free.argtypes = [vp]
@@ -140,6 +141,13 @@ def lib():
     L.plk_ipa_round_lr.argtypes = [vp, u64p, u8p, u64p, u8p, u64p, u64p]
     L.plk_ipa_fold.argtypes = [vp, u64p, u64p]
     L.plk_ipa_read.argtypes = [vp, u64p, u64p, u64p, u8p]
+    L.plk_blake_hash_usize_to_curve.argtypes = [C.c_int, C.c_uint64, sz, u64p]
+    L.plk_blake_hash_usize_to_curve_dev.argtypes = [C.c_int, C.c_uint64, sz, vp, vp]
+    L.plk_blake_hash_base_field_to_curve.argtypes = [C.c_int, u64p, sz, u64p]
+    L.plk_point_compressed_bytes.argtypes = [C.c_int]
+    L.plk_point_compressed_bytes.restype = sz
+    L.plk_points_compress.argtypes = [C.c_int, u64p, u8p, sz, u8p]
+    L.plk_points_decompress.argtypes = [C.c_int, u8p, sz, u64p, u8p, u8p]
     L.plk_kernel_launch_count.restype = C.c_uint64
     L.plk_set_profiling.argtypes = [C.c_int]
     L.plk_msm_last_phase_ms.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
@@ -506,16 +514,23 @@ class HaloIpaRounds:
     read()            -> current (a, b, g_xy, g_zero); after the last fold halo_a[0], halo_b[0], halo_g[0].to_affine()
     """
 
-    def __init__(self, curve: int, a, b, g_xy, g_zero=None):
+    def __init__(self, curve: int, a, b, g_xy=None, g_zero=None, precomputation: "MsmPrecomputation" = None):
         Lb = FIELD_LIMBS[CURVE_BASE_FIELD[curve]]
         a, b = _u64(a).reshape(-1, 4), _u64(b).reshape(-1, 4)
-        g = _u64(g_xy).reshape(-1, 2, Lb)
         n = a.shape[0]
+        self.curve, self.Lb = curve, Lb
+        self.handle = C.c_void_p()
+        self.precomputation = precomputation          # keeps the borrowed table alive
+        if precomputation is not None:
+            # table mode: rounds run against the fixed-base table of pedersen_g, G is never folded
+            if b.shape[0] != n:
+                raise PlonkyPanic("halo_a / halo_b / halo_g length mismatch")
+            _check(lib().plk_ipa_new_with_table(precomputation.handle, _p64(a), _p64(b), n, C.byref(self.handle)))
+            return
+        g = _u64(g_xy).reshape(-1, 2, Lb)
         if b.shape[0] != n or g.shape[0] != n:
             raise PlonkyPanic("halo_a / halo_b / halo_g length mismatch")        # debug_assert_eq!, halo.rs:67-69
         z = _zero_flags(g_zero, n)
-        self.curve, self.Lb = curve, Lb
-        self.handle = C.c_void_p()
         _check(lib().plk_ipa_new(curve, _p64(a), _p64(b), _p64(g), _p8(z), n, C.byref(self.handle)))
 
     def __len__(self):
@@ -534,9 +549,12 @@ class HaloIpaRounds:
         u, u_inv = _u64(u).reshape(4), _u64(u_inv).reshape(4)
         _check(lib().plk_ipa_fold(self.handle, _p64(u), _p64(u_inv)))
 
-    def read(self):
+    def read(self, with_g: bool = True):
         n = len(self)
         a, b = np.zeros((n, 4), dtype=np.uint64), np.zeros((n, 4), dtype=np.uint64)
+        if not with_g:
+            _check(lib().plk_ipa_read(self.handle, _p64(a), _p64(b), None, None))
+            return a, b, None, None
         g = np.zeros((n, 2, self.Lb), dtype=np.uint64)
         z = np.zeros(n, dtype=np.uint8)
         _check(lib().plk_ipa_read(self.handle, _p64(a), _p64(b), _p64(g), _p8(z)))
@@ -552,3 +570,48 @@ class HaloIpaRounds:
             self.close()
         except Exception:
             pass
+
+
+# ------------------------------------------------------------------------------------------------
+# Generator derivation (src/hash_to_curve.rs) and the point wire format (src/serialization.rs)
+# ------------------------------------------------------------------------------------------------
+def blake_hash_usize_to_curve(curve: int, seed_start: int, n: int = 1) -> np.ndarray:
+    """[blake_hash_usize_to_curve::<C>(seed) for seed in seed_start .. seed_start + n] (hash_to_curve.rs:53-76) as
+    (n, 2, L) affine Montgomery limbs -- pedersen_g is seeds 0..degree (circuit_builder.rs:1127)."""
+    Lb = FIELD_LIMBS[CURVE_BASE_FIELD[curve]]
+    out = np.zeros((n, 2, Lb), dtype=np.uint64)
+    _check(lib().plk_blake_hash_usize_to_curve(curve, seed_start, n, _p64(out)))
+    return out
+
+
+def blake_hash_base_field_to_curve(curve: int, seeds) -> np.ndarray:
+    """blake_hash_base_field_to_curve (hash_to_curve.rs:57-76) for (n, L) Montgomery seeds."""
+    Lb = FIELD_LIMBS[CURVE_BASE_FIELD[curve]]
+    s = _u64(seeds).reshape(-1, Lb)
+    out = np.zeros((s.shape[0], 2, Lb), dtype=np.uint64)
+    _check(lib().plk_blake_hash_base_field_to_curve(curve, _p64(s), s.shape[0], _p64(out)))
+    return out
+
+
+def points_to_bytes(curve: int, points_xy, zero=None) -> np.ndarray:
+    """AffinePoint::write (serialization.rs:32-44) per point: (n, 1 + 8 L) bytes."""
+    Lb = FIELD_LIMBS[CURVE_BASE_FIELD[curve]]
+    g = _u64(points_xy).reshape(-1, 2, Lb)
+    n = g.shape[0]
+    z = _zero_flags(zero, n)
+    out = np.zeros((n, 1 + 8 * Lb), dtype=np.uint8)
+    _check(lib().plk_points_compress(curve, _p64(g), _p8(z), n, _p8(out)))
+    return out
+
+
+def points_from_bytes(curve: int, data):
+    """AffinePoint::read (serialization.rs:46-72) per point: ((n, 2, L) limbs, zero flags).  Raises ValueError for
+    "Out of range" / "Invalid x coordinate" (io::Error in the reference)."""
+    Lb = FIELD_LIMBS[CURVE_BASE_FIELD[curve]]
+    d = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1, 1 + 8 * Lb)
+    n = d.shape[0]
+    out = np.zeros((n, 2, Lb), dtype=np.uint64)
+    z = np.zeros(n, dtype=np.uint8)
+    st = np.zeros(n, dtype=np.uint8)
+    _check(lib().plk_points_decompress(curve, _p8(d), n, _p64(out), _p8(z), _p8(st)))
+    return out, z

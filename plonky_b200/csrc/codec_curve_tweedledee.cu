@@ -1,0 +1,3 @@
+// Hash-to-curve / point codec kernels instantiated for one curve (separate translation unit).
+#include "codec_kernels.cuh"
+namespace plk { const CodecOps* codec_ops_tweedledee() { return make_codec_ops<TweedledeeParams>(); } }

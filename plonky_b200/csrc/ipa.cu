@@ -17,6 +17,10 @@ struct plk_ipa_state {
   size_t L = 4;            // u64 limbs of a base-field element
   DevBuf a, b, g;          // n scalars (32 B), n scalars, n affine points (2 * L * 8 B, identity = (0, 0))
   DevBuf partials, io;     // inner-product partials; io: 2 points xyz | 2 flags (8 B each) | 2 inner products | u, u^-1
+  // table mode (plk_ipa_new_with_table): G is never folded, see ipa_kernels.cuh
+  plk_msm_table* table = nullptr;   // borrowed: fixed-base table of the n0 original generators
+  size_t n0 = 0;                    // original length
+  DevBuf coef, sl_sr;               // c_i (n0 scalars); expanded scalars of the L and R MSMs (2 * n0)
 };
 
 namespace {
@@ -78,6 +82,34 @@ int plk_ipa_new(int curve, const uint64_t* a, const uint64_t* b, const uint64_t*
     *out = s.release();
   });
 }
+int plk_ipa_new_with_table(const plk_msm_table* table, const uint64_t* a, const uint64_t* b, size_t n, plk_ipa_state** out) {
+  return guarded([&] {
+    if (!out) fail(PLK_EINVAL, "NULL out");
+    *out = nullptr;
+    if (!table) fail(PLK_EINVAL, "NULL table");
+    if (table->g.variable) fail(PLK_EINVAL, "a fixed-base table is required");
+    if (n != table->n) fail(PLK_ELENGTH, "precomputation / scalars length mismatch");
+    if (!is_pow2(n)) fail(PLK_ENOTPOW2, "Not a power of two");            // log2_strict(degree), halo.rs:62
+    if (!a || !b) fail(PLK_EINVAL, "NULL buffer");
+    std::unique_ptr<plk_ipa_state> s(new plk_ipa_state());
+    s->curve = table->curve;
+    s->n = s->n0 = n;
+    s->L = (size_t)plk_field_limbs(plk_curve_base_field(table->curve));
+    s->table = const_cast<plk_msm_table*>(table);
+    cudaStream_t st = thread_stream();
+    s->a.alloc(n * 32);
+    s->b.alloc(n * 32);
+    s->coef.alloc(n * 32);
+    s->sl_sr.alloc(2 * n * 32);
+    s->partials.alloc(2 * kIpaMaxBlocks * 32);
+    s->io.alloc(1024);
+    PLK_CUDA(cudaMemcpyAsync(s->a.p, a, n * 32, cudaMemcpyHostToDevice, st));
+    PLK_CUDA(cudaMemcpyAsync(s->b.p, b, n * 32, cudaMemcpyHostToDevice, st));
+    ipa_ops_for(s->curve)->init_coef(s->coef.p, n, st);
+    PLK_CUDA(cudaStreamSynchronize(st));
+    *out = s.release();
+  });
+}
 size_t plk_ipa_len(const plk_ipa_state* s) { return s ? s->n : 0; }
 void plk_ipa_free(plk_ipa_state* s) { delete s; }
 
@@ -96,8 +128,14 @@ int plk_ipa_round_lr(plk_ipa_state* s, uint64_t* out_l_xyz, uint8_t* out_l_zero,
     char* d_ip = io + 2 * xyz + 16;           // 2 x 32 bytes
     const char* a = s->a.as<char>();
     const char* g = s->g.as<char>();
-    msm_variable_dev(s->curve, g + half * pb, a, half, d_l, d_flags, st);              // <a_lo, G_hi>  (halo.rs:87)
-    msm_variable_dev(s->curve, g, a + half * 32, half, d_r, d_flags + 8, st);          // <a_hi, G_lo>  (halo.rs:91)
+    if (s->table) {
+      // both MSMs against the fixed-base table of the original generators, forked over the table's side streams
+      ipa_ops_for(s->curve)->expand_scalars(s->a.p, s->coef.p, s->n0, s->n, s->sl_sr.p, st);
+      msm_execute_batch_on(s->table, s->sl_sr.p, 2, d_l, d_flags, st);                 // d_l, d_r adjacent; flags at +0, +1
+    } else {
+      msm_variable_dev(s->curve, g + half * pb, a, half, d_l, d_flags, st);            // <a_lo, G_hi>  (halo.rs:87)
+      msm_variable_dev(s->curve, g, a + half * 32, half, d_r, d_flags + 8, st);        // <a_hi, G_lo>  (halo.rs:91)
+    }
     ipa_ops_for(s->curve)->inner_products(s->a.p, s->b.p, half, s->partials.p, d_ip, st);
     uint8_t flags[16];
     PLK_CUDA(cudaMemcpyAsync(out_l_xyz, d_l, xyz, cudaMemcpyDeviceToHost, st));
@@ -107,7 +145,7 @@ int plk_ipa_round_lr(plk_ipa_state* s, uint64_t* out_l_xyz, uint8_t* out_l_zero,
     PLK_CUDA(cudaMemcpyAsync(out_ip_r, d_ip + 32, 32, cudaMemcpyDeviceToHost, st));
     PLK_CUDA(cudaStreamSynchronize(st));
     *out_l_zero = flags[0];
-    *out_r_zero = flags[8];
+    *out_r_zero = s->table ? flags[1] : flags[8];
   });
 }
 
@@ -120,7 +158,8 @@ int plk_ipa_fold(plk_ipa_state* s, const uint64_t* u, const uint64_t* u_inv) {
     char* d_uu = s->io.as<char>() + 512;
     PLK_CUDA(cudaMemcpyAsync(d_uu, u, 32, cudaMemcpyHostToDevice, st));
     PLK_CUDA(cudaMemcpyAsync(d_uu + 32, u_inv, 32, cudaMemcpyHostToDevice, st));
-    ipa_ops_for(s->curve)->fold(s->a.p, s->b.p, s->g.p, half, d_uu, st);
+    ipa_ops_for(s->curve)->fold(s->a.p, s->b.p, s->table ? nullptr : s->g.p, half, d_uu, st);
+    if (s->table) ipa_ops_for(s->curve)->update_coef(s->coef.p, s->n0, s->n, d_uu, st);
     PLK_CUDA(cudaStreamSynchronize(st));     // u / u_inv are the caller's stack memory
     s->n = half;
   });
@@ -133,6 +172,17 @@ int plk_ipa_read(const plk_ipa_state* s, uint64_t* a, uint64_t* b, uint64_t* g_x
     const size_t pb = 2 * s->L * 8;
     if (a) PLK_CUDA(cudaMemcpyAsync(a, s->a.p, s->n * 32, cudaMemcpyDeviceToHost, st));
     if (b) PLK_CUDA(cudaMemcpyAsync(b, s->b.p, s->n * 32, cudaMemcpyDeviceToHost, st));
+    if (s->table && (g_xy || g_zero)) {
+      // table mode: the folded generators exist only as coefficients; halo_g = sum_i c_i G_i once the length is 1
+      if (s->n != 1) fail(PLK_EINVAL, "table mode materialises halo_g only at length 1");
+      if (!g_xy || !g_zero) fail(PLK_EINVAL, "g_xy and g_zero are read together");
+      char* io = s->io.as<char>();
+      msm_execute_batch_on(s->table, s->coef.p, 1, io, io + 2 * 3 * s->L * 8, st);
+      PLK_CUDA(cudaMemcpyAsync(g_xy, io, pb, cudaMemcpyDeviceToHost, st));      // normalised: (x, y) are the affine coordinates
+      PLK_CUDA(cudaMemcpyAsync(g_zero, io + 2 * 3 * s->L * 8, 1, cudaMemcpyDeviceToHost, st));
+      PLK_CUDA(cudaStreamSynchronize(st));
+      return;
+    }
     if (g_xy) PLK_CUDA(cudaMemcpyAsync(g_xy, s->g.p, s->n * pb, cudaMemcpyDeviceToHost, st));
     if (g_zero) {
       DevBuf dz(s->n, st);

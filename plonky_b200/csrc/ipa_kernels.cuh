@@ -106,9 +106,51 @@ __global__ void __launch_bounds__(128) ipa_fold_points_kernel(void* __restrict__
   store_fp<F>(g, 2 * i + 1, r.y);
 }
 
+// ---- table mode: G is never folded ------------------------------------------------------------------------------
+// With the fixed-base table of the ORIGINAL generators at hand (the prover holds pedersen_g_msm_precomputation,
+// src/plonk.rs:64-69), folding G costs more than it saves: G^(j)[k] = sum over i == k (mod m) of c_i G_i with
+// c_i = prod over the rounds so far of (bit of i selected by that round ? u : u^-1), so
+//   <a_lo, G^(j)_hi> = sum over i with bit (m/2) set    of (a[i & (m/2 - 1)]       c_i) G_i
+//   <a_hi, G^(j)_lo> = sum over i with bit (m/2) clear  of (a[m/2 + (i & (m/2 - 1))] c_i) G_i
+// are two fixed-base MSMs over all n generators (half of the scalars are zero and cost nothing after the digit
+// pass), and the final halo_g is the MSM of the c_i.  Same group elements as halo.rs:87-123, no per-round chain of
+// 255 doublings per generator.
+// sl_sr: 2 * n0 scalars (row 0 = L, row 1 = R); m = current length of a
+template <class C>
+__global__ void ipa_expand_scalars_kernel(const void* __restrict__ a, const void* __restrict__ coef, unsigned long long n0,
+                                          unsigned long long m, void* __restrict__ sl_sr) {
+  typedef Fp<typename C::Scalar> SF;
+  const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (i >= n0) return;
+  const unsigned long long half = m >> 1, k = i & (half - 1);
+  const bool hi = (i & half) != 0;
+  const SF c = load_fp<SF>(coef, i);
+  const SF v = SF::mul(load_fp<SF>(a, hi ? k : half + k), c);
+  store_fp<SF>(sl_sr, i, hi ? v : SF::zero());
+  store_fp<SF>(sl_sr, n0 + i, hi ? SF::zero() : v);
+}
+template <class C>
+__global__ void ipa_init_coef_kernel(void* __restrict__ coef, unsigned long long n0) {
+  typedef Fp<typename C::Scalar> SF;
+  const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (i < n0) store_fp<SF>(coef, i, SF::one());
+}
+// fold of length m -> m/2: c_i *= (bit m/2 of i) ? u : u^-1
+template <class C>
+__global__ void ipa_update_coef_kernel(void* __restrict__ coef, unsigned long long n0, unsigned long long m, const void* __restrict__ uu) {
+  typedef Fp<typename C::Scalar> SF;
+  const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (i >= n0) return;
+  const SF f = load_fp<SF>(uu, (i & (m >> 1)) ? 0 : 1);
+  store_fp<SF>(coef, i, SF::mul(load_fp<SF>(coef, i), f));
+}
+
 struct IpaOps {
   void (*inner_products)(const void* d_a, const void* d_b, size_t half, void* d_partials, void* d_out2, cudaStream_t st);
-  void (*fold)(void* d_a, void* d_b, void* d_g, size_t half, const void* d_uu, cudaStream_t st);
+  void (*fold)(void* d_a, void* d_b, void* d_g, size_t half, const void* d_uu, cudaStream_t st);   // d_g may be NULL (table mode)
+  void (*init_coef)(void* d_coef, size_t n0, cudaStream_t st);
+  void (*expand_scalars)(const void* d_a, const void* d_coef, size_t n0, size_t m, void* d_sl_sr, cudaStream_t st);
+  void (*update_coef)(void* d_coef, size_t n0, size_t m, const void* d_uu, cudaStream_t st);
 };
 constexpr unsigned kIpaMaxBlocks = 296;
 
@@ -125,12 +167,28 @@ template <class C>
 void ipa_fold(void* d_a, void* d_b, void* d_g, size_t half, const void* d_uu, cudaStream_t st) {
   ipa_fold_scalars_kernel<C><<<(unsigned)((half + 127) / 128), 128, 0, st>>>(d_a, d_b, half, d_uu);
   PLK_LAUNCHED();
+  if (!d_g) return;
   ipa_fold_points_kernel<C><<<(unsigned)((half + 127) / 128), 128, 0, st>>>(d_g, half, d_uu);
   PLK_LAUNCHED();
 }
 template <class C>
+void ipa_init_coef(void* d_coef, size_t n0, cudaStream_t st) {
+  ipa_init_coef_kernel<C><<<(unsigned)((n0 + 255) / 256), 256, 0, st>>>(d_coef, n0);
+  PLK_LAUNCHED();
+}
+template <class C>
+void ipa_expand_scalars(const void* d_a, const void* d_coef, size_t n0, size_t m, void* d_sl_sr, cudaStream_t st) {
+  ipa_expand_scalars_kernel<C><<<(unsigned)((n0 + 255) / 256), 256, 0, st>>>(d_a, d_coef, n0, m, d_sl_sr);
+  PLK_LAUNCHED();
+}
+template <class C>
+void ipa_update_coef(void* d_coef, size_t n0, size_t m, const void* d_uu, cudaStream_t st) {
+  ipa_update_coef_kernel<C><<<(unsigned)((n0 + 255) / 256), 256, 0, st>>>(d_coef, n0, m, d_uu);
+  PLK_LAUNCHED();
+}
+template <class C>
 const IpaOps* make_ipa_ops() {
-  static const IpaOps ops = {&ipa_inner_products<C>, &ipa_fold<C>};
+  static const IpaOps ops = {&ipa_inner_products<C>, &ipa_fold<C>, &ipa_init_coef<C>, &ipa_expand_scalars<C>, &ipa_update_coef<C>};
   return &ops;
 }
 }  // namespace plk

@@ -232,6 +232,9 @@ void msm_variable_dev(int curve, const void* d_points_xy, const void* d_scalars,
   }
   delete t;      // stream-ordered frees: the buffers outlive the kernels queued above
 }
+void msm_execute_batch_on(plk_msm_table* t, const void* d_scalars, size_t k, void* d_out_xyz, void* d_out_zero, cudaStream_t st) {
+  run_batch(t, reinterpret_cast<const char*>(d_scalars), k, reinterpret_cast<char*>(d_out_xyz), reinterpret_cast<char*>(d_out_zero), st);
+}
 }  // namespace plk
 
 extern "C" {

@@ -620,11 +620,18 @@ void execute_one(plk_msm_table* t, plk_msm_scratch* s, const void* d_scalars, vo
     // shared-memory histograms per CTA, no global atomics (see msm_hist_kernel)
     const unsigned rows = s->sort_rows, chunk = (unsigned)((g.n + rows - 1) / rows);
     const size_t smem = (size_t)g.nb * 4;
-    static bool attr_done = false;
-    if (!attr_done) {
-      PLK_CUDA(cudaFuncSetAttribute(msm_hist_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortMaxBins * 4));
-      PLK_CUDA(cudaFuncSetAttribute(msm_scatter_smem_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortMaxBins * 4));
-      attr_done = true;
+    {
+      // the opt-in to > 48 KiB of dynamic shared memory is per device (a process may drive several GPUs)
+      static std::mutex attr_mu;
+      static bool attr_done[64] = {};
+      int dev = 0;
+      PLK_CUDA(cudaGetDevice(&dev));
+      std::lock_guard<std::mutex> lk(attr_mu);
+      if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+        PLK_CUDA(cudaFuncSetAttribute(msm_hist_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortMaxBins * 4));
+        PLK_CUDA(cudaFuncSetAttribute(msm_scatter_smem_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortMaxBins * 4));
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
+      }
     }
     msm_hist_kernel<C><<<rows, 1024, smem, st>>>(reinterpret_cast<const uint4*>(d_scalars), g, chunk, s->cta_hist.as<unsigned>());
     PLK_LAUNCHED();

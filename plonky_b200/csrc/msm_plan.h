@@ -76,4 +76,7 @@ struct MsmOps {
 // (identity = (0, 0)) and n Montgomery scalars -> one normalised point (3*L u64) + zero flag, asynchronous on `st`.
 void msm_variable_dev(int curve, const void* d_points_xy, const void* d_scalars, size_t n, void* d_out_xyz, void* d_out_zero,
                       cudaStream_t st);
+// k executes against one fixed-base table on device buffers (k*n scalars, row-major; d_out_xyz k*3*L u64, d_out_zero k
+// bytes), forked over the table's side streams and joined on `st` -- the body of plk_msm_execute_batch_dev.
+void msm_execute_batch_on(plk_msm_table* t, const void* d_scalars, size_t k, void* d_out_xyz, void* d_out_zero, cudaStream_t st);
 }  // namespace plk

@@ -17,7 +17,7 @@ import torch.distributed as dist
 
 from . import lib, _check, FIELD_LIMBS, CURVE_BASE_FIELD, MsmPrecomputation
 
-__all__ = ["msm_precompute_affine_dev", "points_generate_dev", "msm_execute_dev", "msm_execute_sharded", "msm_execute_batch_dev", "fft_dev",
+__all__ = ["msm_precompute_affine_dev", "points_generate_dev", "pedersen_generators_dev", "msm_execute_dev", "msm_execute_sharded", "msm_execute_batch_dev", "fft_dev",
            "DistributedNtt"]
 
 
@@ -30,6 +30,15 @@ def points_generate_dev(curve: int, seed: int, n: int) -> torch.Tensor:
     Lb = FIELD_LIMBS[CURVE_BASE_FIELD[curve]]
     pts = torch.empty((n, 2, Lb), dtype=torch.int64, device="cuda")
     _check(lib().plk_points_generate_dev(curve, seed, n, C.c_void_p(pts.data_ptr()), _stream_ptr()))
+    return pts
+
+
+def pedersen_generators_dev(curve: int, start: int, n: int) -> torch.Tensor:
+    """(n, 2, L) int64 tensor: blake_hash_usize_to_curve(start + i), i < n -- the reference's pedersen_g
+    (src/circuit_builder.rs:1127) derived on the device (src/hash_to_curve.rs:53-76)."""
+    Lb = FIELD_LIMBS[CURVE_BASE_FIELD[curve]]
+    pts = torch.empty((n, 2, Lb), dtype=torch.int64, device="cuda")
+    _check(lib().plk_blake_hash_usize_to_curve_dev(curve, start, n, C.c_void_p(pts.data_ptr()), _stream_ptr()))
     return pts
 
 

@@ -31,6 +31,17 @@ extern "C" {
     fn plk_divide_by_z_h(p: *const plk_fft_plan, coeffs: *const u64, n_in: usize, n_gates: usize, out: *mut u64) -> c_int;
     fn plk_fft_free(p: *mut plk_fft_plan);
     fn plk_batch_inverse(field: c_int, input: *const u64, out: *mut u64, n: usize) -> c_int;
+    // Halo IPA rounds kept on the device (src/halo.rs:63-124)
+    fn plk_ipa_new(curve: c_int, a: *const u64, b: *const u64, g_xy: *const u64, g_zero: *const u8, n: usize, out: *mut *mut plk_ipa_state) -> c_int;
+    fn plk_ipa_new_with_table(t: *const plk_msm_table, a: *const u64, b: *const u64, n: usize, out: *mut *mut plk_ipa_state) -> c_int;
+    fn plk_ipa_round_lr(s: *mut plk_ipa_state, l_xyz: *mut u64, l_zero: *mut u8, r_xyz: *mut u64, r_zero: *mut u8, ip_l: *mut u64, ip_r: *mut u64) -> c_int;
+    fn plk_ipa_fold(s: *mut plk_ipa_state, u: *const u64, u_inv: *const u64) -> c_int;
+    fn plk_ipa_read(s: *const plk_ipa_state, a: *mut u64, b: *mut u64, g_xy: *mut u64, g_zero: *mut u8) -> c_int;
+    fn plk_ipa_free(s: *mut plk_ipa_state);
+    // generator derivation (src/hash_to_curve.rs:53-76) and the point wire format (src/serialization.rs:32-72)
+    fn plk_blake_hash_usize_to_curve(curve: c_int, seed_start: u64, n: usize, points_xy: *mut u64) -> c_int;
+    fn plk_points_compress(curve: c_int, points_xy: *const u64, zero: *const u8, n: usize, out: *mut u8) -> c_int;
+    fn plk_points_decompress(curve: c_int, input: *const u8, n: usize, out_xy: *mut u64, out_zero: *mut u8, out_status: *mut u8) -> c_int;
 }
 
 /// The reference panics on this path (assert_eq! curve_msm.rs:67,106; log2_strict util.rs:16-19;
@@ -188,6 +199,38 @@ pub fn gpu_batch_inverse<F: GpuField>(x: &[F]) -> Vec<F> {
     unpack_fields(&out)
 }
 
+/// halo_a / halo_b / halo_g of batch_opening_proof (halo.rs:53-57) on the device.  `table` = the circuit's
+/// pedersen_g_msm_precomputation: with it G is never folded (plk_ipa_new_with_table).
+#[repr(C)] pub struct plk_ipa_state { _private: [u8; 0] }
+pub struct GpuIpa<C: GpuCurve>(*mut plk_ipa_state, std::marker::PhantomData<C>);
+impl<C: GpuCurve> Drop for GpuIpa<C> { fn drop(&mut self) { unsafe { plk_ipa_free(self.0) } } }
+impl<C: GpuCurve> GpuIpa<C> where C::BaseField: GpuField, C::ScalarField: GpuField {
+    pub fn new(table: *const plk_msm_table, a: &[C::ScalarField], b: &[C::ScalarField]) -> Self {
+        let (pa, pb) = (pack_fields(a), pack_fields(b));
+        let mut s = std::ptr::null_mut();
+        check(unsafe { plk_ipa_new_with_table(table, pa.as_ptr(), pb.as_ptr(), a.len(), &mut s) });
+        GpuIpa(s, std::marker::PhantomData)
+    }
+    /// (msm_parallel(a_lo, g_hi, 8), msm_parallel(a_hi, g_lo, 8), <a_lo, b_hi>, <a_hi, b_lo>)  -- halo.rs:87-93
+    pub fn round_lr(&mut self) -> (ProjectivePoint<C>, ProjectivePoint<C>, C::ScalarField, C::ScalarField) {
+        let l = <C::BaseField as GpuField>::LIMBS;
+        let (mut lx, mut rx, mut lz, mut rz) = (vec![0u64; 3 * l], vec![0u64; 3 * l], 0u8, 0u8);
+        let (mut il, mut ir) = (vec![0u64; 4], vec![0u64; 4]);
+        check(unsafe { plk_ipa_round_lr(self.0, lx.as_mut_ptr(), &mut lz, rx.as_mut_ptr(), &mut rz, il.as_mut_ptr(), ir.as_mut_ptr()) });
+        (unpack_proj::<C>(&lx, lz), unpack_proj::<C>(&rx, rz), GpuField::from_limbs(&il), GpuField::from_limbs(&ir))
+    }
+    /// halo.rs:117-123
+    pub fn fold(&mut self, u: C::ScalarField, u_inv: C::ScalarField) {
+        check(unsafe { plk_ipa_fold(self.0, u.limbs().as_ptr(), u_inv.limbs().as_ptr()) });
+    }
+}
+/// body of `(0..degree).map(blake_hash_usize_to_curve::<C>)` (circuit_builder.rs:1127, verifier.rs:174)
+pub fn gpu_pedersen_generators<C: GpuCurve>(start: usize, n: usize) -> Vec<u64> where C::BaseField: GpuField {
+    let mut xy = vec![0u64; n * 2 * <C::BaseField as GpuField>::LIMBS];
+    check(unsafe { plk_blake_hash_usize_to_curve(C::CURVE_ID, start as u64, n, xy.as_mut_ptr()) });
+    xy          // n x (x, y) Montgomery limbs; AffinePoint::nonzero(x, y) each
+}
+
 // ---- edits in the reference -----------------------------------------------------------------------
 // src/curve/curve_msm.rs
 //   pub struct MsmPrecomputation<C> { generators: Vec<ProjectivePoint<C>>, w: usize, #[serde(skip)] gpu: OnceCell<GpuTable> }
@@ -201,3 +244,8 @@ pub fn gpu_batch_inverse<F: GpuField>(x: &[F]) -> Vec<F> {
 //   pub fn fft_with_precomputation(c, pre)             -> gpu::gpu_fft_padded(.., c)
 // src/polynomial.rs:330  divide_by_z_h -> gpu::gpu_divide_by_z_h;   src/field/field.rs:251 -> gpu::gpu_batch_inverse
 // src/plonk_util.rs:215  commit_polynomials -> gpu::gpu_msm_execute_batch (one call for all polynomials)
+// src/halo.rs:63-124      let mut ipa = gpu::GpuIpa::<C>::new(table, &halo_a, &halo_b); per round: let (l, r, ip_l, ip_r) = ipa.round_lr();
+//                         halo_l_j = l + C::convert(l_j_blinding_factor) * pedersen_h + C::convert(ip_l) * u_prime  (unchanged host code);
+//                         after the challenge: ipa.fold(u_j, u_j_inv); at the end plk_ipa_read gives halo_a[0], halo_b[0], halo_g
+// src/circuit_builder.rs:1127, src/verifier.rs:174   pedersen_g -> gpu::gpu_pedersen_generators::<C>(0, degree)
+// src/serialization.rs:32-72   Vec<AffinePoint<C>> (de)serialisation of proofs / VKs -> plk_points_compress / plk_points_decompress

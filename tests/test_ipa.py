@@ -96,6 +96,71 @@ def test_device_rounds_match_restatement(curve, n):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("curve,n", [(po.TWEEDLEDEE, 64), (po.TWEEDLEDUM, 16), (po.BLS12_377, 8)], ids=lambda v: getattr(v, "name", str(v)))
+def test_table_mode_rounds_match_restatement(curve, n):
+    """plk_ipa_new_with_table: G is never folded (coefficients over the original generators + fixed-base MSMs);
+    every L_j, R_j, inner product, folded a / b and the final halo_g must equal the folding restatement's."""
+    import plonky_b200 as pk
+    a, b, g = make_inputs(curve, n, 19, special=True)
+    A, B, G, Z = pack(curve, a, b, g)
+    pre = pk.msm_precompute_affine(curve.cid, G, 11, zero=Z)
+    st = pk.HaloIpaRounds(curve.cid, A, B, precomputation=pre)
+    rnd = 0
+    while len(st) > 1:
+        (l, lz), (r, rz), ipl, ipr = st.round_lr()
+        (wl, wlz), (wr, wrz), wipl, wipr = rp.ipa_round_lr(curve.cid, A, B, G, Z)
+        assert lz == wlz and rz == wrz
+        assert np.array_equal(l[:2], wl) and np.array_equal(r[:2], wr)
+        assert np.array_equal(ipl, wipl) and np.array_equal(ipr, wipr)
+        u, u_inv = challenge(curve, 50 + rnd)
+        U, UI = mont_array(curve.scalar, [u])[0], mont_array(curve.scalar, [u_inv])[0]
+        st.fold(U, UI)
+        A, B, G, Z = rp.ipa_fold(curve.cid, A, B, G, Z, U, UI)
+        ga, gb, _, _ = st.read(with_g=False)
+        assert np.array_equal(ga, A) and np.array_equal(gb, B)
+        if len(st) > 1:
+            with pytest.raises(ValueError):          # the folded generators are only materialised at length 1
+                st.read()
+        rnd += 1
+    ga, gb, gg, gz = st.read()
+    assert np.array_equal(ga, A) and np.array_equal(gb, B)
+    assert np.array_equal(gz, Z) and np.array_equal(gg, G)          # halo_g[0].to_affine(), halo.rs:126-127
+
+
+@pytest.mark.gpu
+def test_table_mode_matches_folding_mode_2p10():
+    """Both device paths on the same inputs at n = 2^10 (Tweedledee, reference generator set)."""
+    import plonky_b200 as pk
+    curve = po.TWEEDLEDEE
+    sf = curve.scalar
+    n = 1 << 10
+    A = mont_array(sf, rand_scalars(sf, 61, n))
+    B = mont_array(sf, rand_scalars(sf, 62, n))
+    G = pk.blake_hash_usize_to_curve(curve.cid, 0, n)           # pedersen_g, circuit_builder.rs:1127
+    pre = pk.msm_precompute_affine(curve.cid, G, 11)
+    s1 = pk.HaloIpaRounds(curve.cid, A, B, G)
+    s2 = pk.HaloIpaRounds(curve.cid, A, B, precomputation=pre)
+    rnd = 0
+    while len(s1) > 1:
+        r1, r2 = s1.round_lr(), s2.round_lr()
+        for x, y in zip(r1, r2):
+            if isinstance(x, tuple):
+                assert x[1] == y[1] and np.array_equal(x[0], y[0])
+            else:
+                assert np.array_equal(x, y)
+        u, u_inv = challenge(curve, 70 + rnd)
+        U, UI = mont_array(sf, [u])[0], mont_array(sf, [u_inv])[0]
+        s1.fold(U, UI)
+        s2.fold(U, UI)
+        rnd += 1
+    f1, f2 = s1.read(), s2.read()
+    for x, y in zip(f1, f2):
+        assert np.array_equal(x, y)
+    with pytest.raises(pk.PlonkyPanic):               # table length != vector length
+        pk.HaloIpaRounds(curve.cid, A[:512], B[:512], precomputation=pre)
+
+
+@pytest.mark.gpu
 def test_device_rounds_errors():
     import plonky_b200 as pk
     curve = po.TWEEDLEDEE
