@@ -198,7 +198,7 @@ def run_reference(args):
         "e2e": {"value": base["value"], "unit": "scalar-muls/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -363,7 +363,7 @@ def run_ours(args):
         if "ntt" in line:
             line["ntt"]["cpu_baseline"] = cpu_ntt_baseline(log_n=20)
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -463,7 +463,27 @@ def bench_ntt_domain_split(args, pk, pkd, torch, np, dist, world, rank):
                        "all_to_all_bytes_sent_per_rank": bytes_a2a, "log_r1": d.log_r1}}
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries write to fd 1 (NCCL prints its version banner there): send fd 1 to stderr for the run and keep the
+    real stdout for the ONE JSON line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -26,6 +26,7 @@
 // Roofline accounting: algorithmic bytes = n * (32 + 2 * 8L); the table walk reads
 // nwin * 2 * 8L bytes per term instead of one point (the reference streams its table the same way).
 #pragma once
+#include <stdlib.h>
 #include "msm_plan.h"
 #include "ec.cuh"
 
@@ -251,9 +252,11 @@ __global__ void __launch_bounds__(kAccThreads) msm_accumulate_kernel(const void*
 }
 
 // The three tail kernels below run one QUAD (4 lanes) per logical work item, see QuadXYZZ in ec.cuh.
+// One thread per bucket.  (Measured alternatives, all slower at 2^15 buckets x 16 partials: four lanes per bucket with a
+// shuffle butterfly 0.27 ms, one quad per bucket with QuadXYZZ 0.27 ms, vs 0.20 ms here.)
 template <class C>
 __global__ void msm_bucket_sum_kernel(const void* __restrict__ partials, const unsigned* __restrict__ task_off, unsigned nb,
-                                      void* __restrict__ buckets, unsigned* __restrict__ big_list) {
+                                             void* __restrict__ buckets, unsigned* __restrict__ big_list) {
   const unsigned b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
   const unsigned t0 = task_off[b], t1 = task_off[b + 1];
@@ -261,8 +264,6 @@ __global__ void msm_bucket_sum_kernel(const void* __restrict__ partials, const u
     big_list[1 + atomicAdd(&big_list[0], 1u)] = b;
     return;
   }
-  // (four lanes per bucket with a shuffle butterfly was measured slower: 0.27 vs 0.22 ms -- the tails pay per warp
-  // instruction, not per active lane)
   XYZZ<C> acc = XYZZ<C>::identity();
   for (unsigned t = t0; t < t1; ++t) acc = XYZZ<C>::add(acc, load_xyzz<C>(partials, t));
   store_xyzz<C>(buckets, b, acc);
@@ -296,55 +297,61 @@ __global__ void __launch_bounds__(256) msm_big_bucket_kernel(const void* __restr
 // bucket index b carries weight (b + 1).  Range [lo, lo + R): sum_b (b + 1) B_b =
 //   sum_b (b - lo + 1) B_b  (running sum, curve_msm.rs:149-154)  +  lo * sum_b B_b
 template <class C>
-__global__ void msm_range_kernel(const void* __restrict__ buckets, unsigned nb, unsigned nbw, void* __restrict__ range_out) {
+__global__ void __launch_bounds__(kQuadThreads) msm_range_kernel(const void* __restrict__ buckets, unsigned nb, unsigned nbw,
+                                                                void* __restrict__ range_out) {
+  typedef QuadXYZZ<C> Q;
+  __shared__ uint4 quad_sm[(kQuadThreads / 4) * Q::kSmemVec];
+  typename Q::Ctx qc = Q::make_ctx(quad_sm);
   const unsigned r = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
-  const int ql = threadIdx.x & 3;
-  const unsigned qmask = 0xFu << (threadIdx.x & 28);
   const unsigned lo = r * kRangeSize;
   if (lo >= nb) return;
   unsigned hi = lo + kRangeSize;
   if (hi > nb) hi = nb;
   XYZZ<C> run = XYZZ<C>::identity(), sum = XYZZ<C>::identity();
   for (unsigned b = hi; b-- > lo;) {
-    run = QuadXYZZ<C>::add(run, load_xyzz<C>(buckets, b), ql, qmask);
-    sum = QuadXYZZ<C>::add(sum, run, ql, qmask);
+    run = Q::add(run, load_xyzz<C>(buckets, b), qc);
+    sum = Q::add(sum, run, qc);
   }
   const unsigned wlo = lo & (nbw - 1);            // index inside its window's bucket set (ranges never straddle windows)
-  if (wlo != 0 && !run.is_identity()) sum = QuadXYZZ<C>::add(sum, QuadXYZZ<C>::mul_u64(run, wlo, ql, qmask), ql, qmask);
-  if (ql == 0) store_xyzz<C>(range_out, r, sum);
+  if (wlo != 0 && !run.is_identity()) sum = Q::add(sum, Q::mul_u64(run, wlo, qc), qc);
+  if (qc.ql == 0) store_xyzz<C>(range_out, r, sum);
 }
 
 // out[i] = sum of in[i * chunk .. min(count, (i + 1) * chunk)), one quad per output
 template <class C>
-__global__ void msm_sum_chunks_kernel(const void* __restrict__ in, unsigned count, unsigned chunk, void* __restrict__ out) {
+__global__ void __launch_bounds__(kQuadThreads) msm_sum_chunks_kernel(const void* __restrict__ in, unsigned count, unsigned chunk,
+                                                                     void* __restrict__ out) {
+  typedef QuadXYZZ<C> Q;
+  __shared__ uint4 quad_sm[(kQuadThreads / 4) * Q::kSmemVec];
+  typename Q::Ctx qc = Q::make_ctx(quad_sm);
   const unsigned i = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
-  const int ql = threadIdx.x & 3;
-  const unsigned qmask = 0xFu << (threadIdx.x & 28);
   const unsigned lo = i * chunk;
   if (lo >= count) return;
   unsigned hi = lo + chunk;
   if (hi > count) hi = count;
   XYZZ<C> acc = load_xyzz<C>(in, lo);
-  for (unsigned j = lo + 1; j < hi; ++j) acc = QuadXYZZ<C>::add(acc, load_xyzz<C>(in, j), ql, qmask);
-  if (ql == 0) store_xyzz<C>(out, i, acc);
+  for (unsigned j = lo + 1; j < hi; ++j) acc = Q::add(acc, load_xyzz<C>(in, j), qc);
+  if (qc.ql == 0) store_xyzz<C>(out, i, acc);
 }
 
 // single CTA of (blockDim / 4) quads: sum `count` XYZZ points; optionally normalise to (x, y, z = 1 | zero flag)
 template <class C>
-__global__ void msm_final_kernel(const void* __restrict__ in, unsigned count, void* __restrict__ out_xyzz,
-                                 uint32_t* __restrict__ out_xyz, unsigned char* __restrict__ out_zero) {
+__global__ void __launch_bounds__(4 * kFinalQuadsMax) msm_final_kernel(const void* __restrict__ in, unsigned count, void* __restrict__ out_xyzz,
+                                                                      uint32_t* __restrict__ out_xyz, unsigned char* __restrict__ out_zero) {
   typedef Fp<typename C::Base> F;
+  typedef QuadXYZZ<C> Q;
   extern __shared__ uint4 sm[];
+  __shared__ uint4 quad_sm[kFinalQuadsMax * Q::kSmemVec];
+  typename Q::Ctx qc = Q::make_ctx(quad_sm);
   const unsigned q = threadIdx.x >> 2, nq = blockDim.x >> 2;
-  const int ql = threadIdx.x & 3;
-  const unsigned qmask = 0xFu << (threadIdx.x & 28);
+  const int ql = qc.ql;
   XYZZ<C> acc = XYZZ<C>::identity();
-  for (unsigned i = q; i < count; i += nq) acc = QuadXYZZ<C>::add(acc, load_xyzz<C>(in, i), ql, qmask);
+  for (unsigned i = q; i < count; i += nq) acc = Q::add(acc, load_xyzz<C>(in, i), qc);
   if (ql == 0) store_xyzz<C>(sm, q, acc);
   __syncthreads();
   for (unsigned d = nq >> 1; d > 0; d >>= 1) {
     XYZZ<C> s;
-    if (q < d) s = QuadXYZZ<C>::add(load_xyzz<C>(sm, q), load_xyzz<C>(sm, q + d), ql, qmask);
+    if (q < d) s = Q::add(load_xyzz<C>(sm, q), load_xyzz<C>(sm, q + d), qc);
     __syncthreads();
     if (q < d && ql == 0) store_xyzz<C>(sm, q, s);
     __syncthreads();
@@ -371,12 +378,13 @@ template <class C>
 __global__ void msm_window_combine_kernel(const void* __restrict__ window_sums, int nwin, int c, void* __restrict__ out_xyzz,
                                           uint32_t* __restrict__ out_xyz, unsigned char* __restrict__ out_zero) {
   typedef Fp<typename C::Base> F;
-  const int ql = threadIdx.x & 3;
-  const unsigned qmask = 0xFu;
+  typedef QuadXYZZ<C> Q;
+  __shared__ uint4 quad_sm[Q::kSmemVec];          // launched with one quad
+  typename Q::Ctx qc = Q::make_ctx(quad_sm);
   XYZZ<C> acc = load_xyzz<C>(window_sums, nwin - 1);
   for (int j = nwin - 2; j >= 0; --j) {
-    for (int k = 0; k < c; ++k) acc = QuadXYZZ<C>::dbl(acc, ql, qmask);
-    acc = QuadXYZZ<C>::add(acc, load_xyzz<C>(window_sums, j), ql, qmask);
+    for (int k = 0; k < c; ++k) acc = Q::dbl(acc, qc);
+    acc = Q::add(acc, load_xyzz<C>(window_sums, j), qc);
   }
   if (threadIdx.x == 0) {
     if (out_xyzz) store_xyzz<C>(out_xyzz, 0, acc);
@@ -673,7 +681,7 @@ void execute_one(plk_msm_table* t, plk_msm_scratch* s, const void* d_scalars, vo
   PLK_LAUNCHED();
   s->timer.mark(st);
   const unsigned nranges = (g.nb + kRangeSize - 1) / kRangeSize;
-  msm_range_kernel<C><<<(4 * nranges + 63) / 64, 64, 0, st>>>(s->buckets.p, g.nb, g.nbw, s->ranges.p);
+  msm_range_kernel<C><<<(4 * nranges + kQuadThreads - 1) / kQuadThreads, kQuadThreads, 0, st>>>(s->buckets.p, g.nb, g.nbw, s->ranges.p);
   PLK_LAUNCHED();
   s->timer.mark(st);
   const void* fin = s->ranges.p;
@@ -681,7 +689,7 @@ void execute_one(plk_msm_table* t, plk_msm_scratch* s, const void* d_scalars, vo
   auto chunk_pass = [&](unsigned chunk) {
     const unsigned nout = (fcount + chunk - 1) / chunk;
     void* dst = (fin == s->partials.p) ? s->buckets.p : s->partials.p;     // ping-pong between consumed buffers
-    msm_sum_chunks_kernel<C><<<(4 * nout + 63) / 64, 64, 0, st>>>(fin, fcount, chunk, dst);
+    msm_sum_chunks_kernel<C><<<(4 * nout + kQuadThreads - 1) / kQuadThreads, kQuadThreads, 0, st>>>(fin, fcount, chunk, dst);
     PLK_LAUNCHED();
     fin = dst;
     fcount = nout;

@@ -9,6 +9,8 @@ constexpr int kTaskSizeMax = 32;     // S: additions per accumulate task (smalle
 constexpr int kBigBucket = 32;       // buckets with more task partials than this are summed by a whole CTA
 constexpr int kRangeSize = 8;        // buckets per running-sum range
 constexpr int kAccThreads = 128;
+constexpr int kQuadThreads = 64;     // CTA size of the quad-cooperative tail kernels (16 quads)
+constexpr int kFinalQuadsMax = 64;   // quads of the single-CTA final reduction
 constexpr unsigned kSortMaxBins = 32768;   // shared-memory histogram sort: nb * 4 B <= 128 KiB
 
 struct MsmGeom {
