@@ -279,6 +279,9 @@ uint64_t plk_kernel_launch_count(void);
  * synchronise on the last event and return the number of phases written (negative status on error).
  * MSM phases: count, scan, scatter, accumulate, bucket_sum, range, final.  NTT: one phase per pass. */
 int plk_set_profiling(int enabled);
+/* Montgomery products per second the device sustains in `field` (4 independent dependent chains per thread, one
+ * resident wave): the arithmetic ceiling the MSM / NTT kernels are quoted against beside the HBM roofline. */
+int plk_measure_mul_throughput(int field, double* products_per_s);
 int plk_msm_last_phase_ms(const plk_msm_table* t, float* out_ms, int cap);
 int plk_fft_last_pass_ms(const plk_fft_plan* p, float* out_ms, int cap);
 int plk_fft_num_passes(const plk_fft_plan* p);

@@ -150,6 +150,7 @@ def lib():
     L.plk_points_decompress.argtypes = [C.c_int, u8p, sz, u64p, u8p, u8p]
     L.plk_kernel_launch_count.restype = C.c_uint64
     L.plk_set_profiling.argtypes = [C.c_int]
+    L.plk_measure_mul_throughput.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.plk_msm_last_phase_ms.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
     L.plk_fft_last_pass_ms.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
     L.plk_fft_num_passes.argtypes = [vp]
@@ -199,6 +200,13 @@ MSM_PHASES = ("count", "scan", "scatter", "accumulate", "bucket_sum", "range", "
 def set_profiling(enabled: bool):
     """Record CUDA events between the kernels of every MSM execute / transform (measurement only)."""
     lib().plk_set_profiling(1 if enabled else 0)
+
+
+def measure_mul_throughput(field: int) -> float:
+    """Montgomery products / s the device sustains in `field` (measurement only)."""
+    v = C.c_double()
+    _check(lib().plk_measure_mul_throughput(field, C.byref(v)))
+    return float(v.value)
 
 
 def msm_last_phase_ms(pre: "MsmPrecomputation"):

@@ -110,6 +110,53 @@ __global__ void batch_inverse_kernel(const void* in, void* out, unsigned long lo
   }
 }
 
+// Throughput probe: every thread runs 4 independent chains of dependent Montgomery products (the ILP of a mixed
+// point addition).  bench.py quotes the MSM / NTT kernels against this measured products/s ceiling next to the HBM
+// roofline (tools/bench_mul.cu is the standalone version).
+template <class P>
+__global__ void __launch_bounds__(128) mul_throughput_kernel(int iters, uint32_t* out) {
+  typedef Fp<P> F;
+  F a[4], b = F::one();
+  for (int k = 0; k < F::N - 1; ++k) {
+    b.l[k] ^= threadIdx.x * 2654435761u + k;
+    for (int c = 0; c < 4; ++c) a[c].l[k] = 0x9e3779b9u * (k + 1) + c + blockIdx.x;
+  }
+  for (int c = 0; c < 4; ++c) a[c].l[F::N - 1] = 1;          // operands stay below p
+  b.l[F::N - 1] = 2;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) a[c] = F::mul(a[c], b);
+  }
+  uint32_t acc = 0;
+  for (int c = 0; c < 4; ++c) for (int k = 0; k < F::N; ++k) acc ^= a[c].l[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+template <class P>
+void measure_mul_throughput(double* products_per_s, cudaStream_t st) {
+  int dev = 0, sms = 0;
+  PLK_CUDA(cudaGetDevice(&dev));
+  PLK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int blocks = sms * 4, threads = 128, iters = 1000;
+  DevBuf out((size_t)blocks * threads * 4, st);
+  cudaEvent_t e0, e1;
+  PLK_CUDA(cudaEventCreate(&e0));
+  PLK_CUDA(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {              // rep 0 is the warm-up
+    PLK_CUDA(cudaEventRecord(e0, st));
+    mul_throughput_kernel<P><<<blocks, threads, 0, st>>>(iters, out.as<uint32_t>());
+    PLK_LAUNCHED();
+    PLK_CUDA(cudaEventRecord(e1, st));
+    PLK_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    PLK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *products_per_s = (double)blocks * threads * iters * 4 / (best * 1e-3);
+}
+
 template <class P>
 void launch_field_op(int op, const void* a, const void* b, void* out, size_t n, cudaStream_t st) {
   if (n == 0) return;
@@ -222,6 +269,14 @@ int plk_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64
     PLK_FIELD_DISPATCH(field, launch_field_op, op, da, b ? db : nullptr, dout, n, st);
     PLK_CUDA(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, st));
     PLK_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+int plk_measure_mul_throughput(int field, double* products_per_s) {
+  return guarded([&] {
+    if (!products_per_s) fail(PLK_EINVAL, "NULL out");
+    cudaStream_t st = thread_stream();
+    PLK_FIELD_DISPATCH(field, measure_mul_throughput, products_per_s, st);
   });
 }
 
