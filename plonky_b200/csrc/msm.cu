@@ -39,11 +39,14 @@ int pick_window(size_t n) {
     int c = atoi(e);
     if (c >= 2 && c <= 24) return c;
   }
+  // Measured on B200 (execute, ms; c = 13 / 14 / 15 / 16):  2^10: .34 .59 .36 .39   2^12: .41 .44 .39 .45
+  // 2^14: .59 .53 .45 -   2^16: .80 .74 .61 .63   2^18: 4.3 1.43 1.16 1.19   2^20: 16 wins (fewer windows).
+  // Small windows leave hundreds of entries per bucket, i.e. many task partials per bucket for the bucket-sum
+  // kernel; the running-sum tails cost ~0.27 ms whatever the bucket count, so up to 2^18 terms 15 bits are best.
   int lg = log2_ceil(n ? n : 1);
-  int c = lg - 1;
-  if (c < 4) c = 4;
-  if (c > 16) c = 16;
-  return c;
+  if (lg >= 19) return 16;
+  if (lg >= 11) return 15;
+  return 13;
 }
 
 // variable base (msm_parallel): every window has its own buckets, so the reduction work is nwin * 2^c

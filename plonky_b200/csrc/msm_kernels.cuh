@@ -66,7 +66,8 @@ __global__ void msm_count_kernel(const uint4* __restrict__ scalars, MsmGeom g, u
 
 // single CTA: offsets[b] = exclusive sum of counts, task_off[b] = exclusive sum of ceil(count / S);
 // offsets[nb] / task_off[nb] = totals; cursors[b] = offsets[b] (scatter positions).  1024 entries per
-// step: warp-shuffle scans, one shared-memory hop for the 32 warp totals.
+// step: warp-shuffle scans, one shared-memory hop for the 32 warp totals.  (One contiguous strip per thread + a single
+// block scan was measured slower: 0.106 vs 0.036 ms at 2^15 buckets -- strided, latency-bound loads from one CTA.)
 static __global__ void msm_scan_kernel(const unsigned* __restrict__ counts, unsigned nb, unsigned task, unsigned* __restrict__ offsets,
                                        unsigned* __restrict__ task_off, unsigned* __restrict__ cursors) {
   __shared__ unsigned w_a[32], w_b[32];
@@ -252,21 +253,34 @@ __global__ void __launch_bounds__(kAccThreads) msm_accumulate_kernel(const void*
 }
 
 // The three tail kernels below run one QUAD (4 lanes) per logical work item, see QuadXYZZ in ec.cuh.
-// One thread per bucket.  (Measured alternatives, all slower at 2^15 buckets x 16 partials: four lanes per bucket with a
-// shuffle butterfly 0.27 ms, one quad per bucket with QuadXYZZ 0.27 ms, vs 0.20 ms here.)
+// Two lanes per bucket: lane h sums the task partials t0 + h, t0 + h + 2, ..., one full-warp shuffle exchanges the two
+// halves and both lanes add them (lane 0 stores).  No lane leaves before the shuffle, so the full mask is legal and
+// the exchange is 32 plain SHFLs.  Half the dependent chain and twice the warps of one thread per bucket.
+// (Measured alternatives at 2^15 buckets x 16 partials: one thread per bucket 0.20 ms; four lanes with quad-mask
+// shuffles 0.27 ms; one QuadXYZZ quad per bucket 0.27 ms.)
 template <class C>
-__global__ void msm_bucket_sum_kernel(const void* __restrict__ partials, const unsigned* __restrict__ task_off, unsigned nb,
-                                             void* __restrict__ buckets, unsigned* __restrict__ big_list) {
-  const unsigned b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nb) return;
-  const unsigned t0 = task_off[b], t1 = task_off[b + 1];
-  if (t1 - t0 > kBigBucket) {            // skewed digit distribution: leave it to msm_big_bucket_kernel
-    big_list[1 + atomicAdd(&big_list[0], 1u)] = b;
-    return;
-  }
+__global__ void __launch_bounds__(128) msm_bucket_sum_kernel(const void* __restrict__ partials, const unsigned* __restrict__ task_off, unsigned nb,
+                                                            void* __restrict__ buckets, unsigned* __restrict__ big_list) {
+  typedef Fp<typename C::Base> F;
+  const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned b = gid >> 1, h = gid & 1;
+  const bool valid = b < nb;
+  const unsigned t0 = valid ? task_off[b] : 0u, t1 = valid ? task_off[b + 1] : 0u;
+  const bool big = t1 - t0 > kBigBucket;            // skewed digit distribution: leave it to msm_big_bucket_kernel
   XYZZ<C> acc = XYZZ<C>::identity();
-  for (unsigned t = t0; t < t1; ++t) acc = XYZZ<C>::add(acc, load_xyzz<C>(partials, t));
-  store_xyzz<C>(buckets, b, acc);
+  if (!big)
+    for (unsigned t = t0 + h; t < t1; t += 2) acc = XYZZ<C>::add(acc, load_xyzz<C>(partials, t));
+  XYZZ<C> other;
+#pragma unroll
+  for (int k = 0; k < F::N; ++k) {
+    other.x.l[k] = __shfl_xor_sync(0xffffffffu, acc.x.l[k], 1);
+    other.y.l[k] = __shfl_xor_sync(0xffffffffu, acc.y.l[k], 1);
+    other.zz.l[k] = __shfl_xor_sync(0xffffffffu, acc.zz.l[k], 1);
+    other.zzz.l[k] = __shfl_xor_sync(0xffffffffu, acc.zzz.l[k], 1);
+  }
+  if (!valid || h != 0) return;
+  if (big) { big_list[1 + atomicAdd(&big_list[0], 1u)] = b; return; }
+  store_xyzz<C>(buckets, b, XYZZ<C>::add(acc, other));
 }
 // Buckets holding very many entries (all scalars equal, a short top window, ...): one CTA per bucket, strided
 // partial sums per thread + shared-memory tree, so that the worst case stays a log-depth reduction.
@@ -674,7 +688,7 @@ void execute_one(plk_msm_table* t, plk_msm_scratch* s, const void* d_scalars, vo
                                                             s->task_off.as<unsigned>(), g.nb, g.task, s->partials.p);
   PLK_LAUNCHED();
   s->timer.mark(st);
-  msm_bucket_sum_kernel<C><<<(g.nb + 127) / 128, 128, 0, st>>>(s->partials.p, s->task_off.as<unsigned>(), g.nb, s->buckets.p,
+  msm_bucket_sum_kernel<C><<<(2 * g.nb + 127) / 128, 128, 0, st>>>(s->partials.p, s->task_off.as<unsigned>(), g.nb, s->buckets.p,
                                                                s->big_list.as<unsigned>());
   PLK_LAUNCHED();
   msm_big_bucket_kernel<C><<<64, 256, 256 * xyzz, st>>>(s->partials.p, s->task_off.as<unsigned>(), s->buckets.p, s->big_list.as<unsigned>());
