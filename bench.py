@@ -367,6 +367,12 @@ def run_ours(args):
         res = bench_ntt_domain_split(args, pk, pkd, torch, np, dist, world, rank)
         if rank == 0:
             line["ntt"] = res
+    # ---- secondary: the Halo IPA rounds of one opening proof at the prover's size (table mode), N = 1 only ----
+    if world == 1 and not args.skip_ntt:
+        try:
+            line["ipa"] = bench_ipa(pk, np, curve, 16)
+        except Exception as e:                       # an extra, never a reason to lose the bench line
+            line["ipa"] = {"error": str(e)}
     if rank == 0:
         line["clocks"] = sampler.stop()
         line["clocks"]["window"] = "warm-up + timed steps + per-kernel loop + e2e (+ NTT section at N=1), 100 ms polling"
@@ -379,6 +385,36 @@ def run_ours(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def bench_ipa(pk, np, curve, log_n):
+    """All log2(n) rounds of batch_opening_proof's loop (halo.rs:63-124) through the C ABI, table mode: per round two
+    fixed-base MSMs + two inner products come back to the host and one challenge goes in (host wall clock)."""
+    n = 1 << log_n
+    a, b = rand_scalars_np(n, SEED + 31), rand_scalars_np(n, SEED + 32)
+    if curve == 2:
+        a[:, 3] >>= np.uint64(2)
+        b[:, 3] >>= np.uint64(2)
+    g = pk.blake_hash_usize_to_curve(curve, 0, n)
+    pre = pk.msm_precompute_affine(curve, g, 11)
+    sf = pk.CURVE_SCALAR_FIELD[curve]
+    u = rand_scalars_np(1, SEED + 33)[0]
+    if curve == 2:
+        u[3] >>= np.uint64(2)
+    u_inv = pk.field_op(sf, "inverse", u.reshape(1, 4))[0]
+    best = None
+    for _ in range(3):
+        st = pk.HaloIpaRounds(curve, a, b, precomputation=pre)
+        t0 = time.perf_counter()
+        while len(st) > 1:
+            st.round_lr()
+            st.fold(u, u_inv)
+        st.read()
+        dt = (time.perf_counter() - t0) * 1e3
+        best = dt if best is None else min(best, dt)
+        st.close()
+    return {"workload": f"Halo IPA rounds, n = 2^{log_n}, table mode (G never folded), {log_n} rounds + final halo_g",
+            "ms_all_rounds": best, "ms_per_round": best / log_n, "timing": "host wall clock over the synchronous C-ABI calls, best of 3"}
 
 
 def bench_ntt(args, pk, pkd, torch, np, hbm_peak, peak_kind):

@@ -163,6 +163,25 @@ int plk_coset_ifft(const plk_fft_plan* p, const uint64_t* evals, const uint64_t*
 int plk_divide_by_z_h(const plk_fft_plan* p, const uint64_t* coeffs, size_t n_in, size_t n_gates,
                       uint64_t* out);
 
+/* Polynomial::mul (src/polynomial.rs:209-227): out = a * b as 2^log2_ceil(deg a + deg b + 1) coefficients
+ * (*out_len; the reference returns the un-trimmed IFFT output), or the single coefficient 0 when either operand is
+ * zero.  Trailing zero coefficients of a and b are ignored like Polynomial::degree does.  out_cap elements must be
+ * available (PLK_ESIZE otherwise).  The per-call fft_precompute of the reference (:217) becomes a cached plan. */
+int plk_poly_mul(int field, const uint64_t* a, size_t na, const uint64_t* b, size_t nb, uint64_t* out,
+                 size_t out_cap, size_t* out_len);
+
+/* permutation_polynomial (src/plonk_util.rs:233-262): the values of Plonk's Z on the subgroup.
+ *   out[0] = 1,  out[i] = out[i-1] * prod_j (w(i-1, j) + beta k_j x_{i-1} + gamma) / prod_j (w(i-1, j) + beta s_j(i-1) + gamma)
+ * for j < num_routed (NUM_ROUTED_WIRES = 6, src/plonk.rs:22).  subgroup: degree elements x_i; wires: Witness::wire_values
+ * row-major, wire (i, j) at i * wire_stride + j (wire_stride = NUM_WIRES = 9); sigma: num_routed rows of sigma_row_len
+ * elements, s_j(i) at sigma_stride * i (the reference reads the 8n-point LDE with stride 8, :252); k_is: the routed
+ * shifts get_subgroup_shift(j) (they come from a seeded ChaCha RNG in the reference: caller-supplied); beta, gamma.
+ * One thread per gate, Montgomery's trick for the n divisions, prefix-product scan.  PLK_EZERO if a denominator is 0. */
+int plk_permutation_polynomial(int field, size_t degree, unsigned num_routed, const uint64_t* subgroup,
+                               const uint64_t* wires, size_t wire_stride, const uint64_t* sigma,
+                               size_t sigma_row_len, size_t sigma_stride, const uint64_t* k_is,
+                               const uint64_t* beta, const uint64_t* gamma, uint64_t* out);
+
 /* Device-resident variants: d_in / d_out hold n_in resp. `size` elements per row, k rows.
  * flags: bit0 inverse, bit1 coset shift by the field generator on the coefficient side. */
 #define PLK_FFT_INVERSE 1u

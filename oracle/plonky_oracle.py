@@ -606,6 +606,43 @@ def point_from_bytes(curve: Curve, data: bytes) -> Affine:
     return (x, y) if (y & 1) == ((mask & 2) >> 1) else (x, (-y) % f.p)
 
 
+def poly_mul(field: Field, a: Sequence[int], b: Sequence[int]) -> List[int]:
+    """Polynomial::mul (src/polynomial.rs:209-227) on canonical ints: schoolbook product, returned with the length the
+    reference's FFT path produces (2^log2_ceil(deg a + deg b + 1), or [0] for a zero operand)."""
+    def trim(x):
+        x = [v % field.p for v in x]
+        while x and x[-1] == 0:
+            x.pop()
+        return x
+    a, b = trim(a), trim(b)
+    if not a or not b:
+        return [0]
+    size = len(a) + len(b) - 1
+    out = [0] * (1 << log2_ceil(size))
+    for i, x in enumerate(a):
+        for j, y in enumerate(b):
+            out[i + j] = (out[i + j] + x * y) % field.p
+    return out
+
+
+def permutation_polynomial(field: Field, subgroup: Sequence[int], wire_values, sigma_values, k_is: Sequence[int], beta: int, gamma: int,
+                           num_routed: int = 6, sigma_stride: int = 8) -> List[int]:
+    """src/plonk_util.rs:233-262 on canonical ints: wire_values[i][j], sigma_values[j][sigma_stride * i]."""
+    p = field.p
+    z = [1]
+    for i in range(1, len(subgroup)):
+        x = subgroup[i - 1]
+        num = den = 1
+        for j in range(num_routed):
+            w = wire_values[i - 1][j]
+            num = num * (w + beta * k_is[j] * x + gamma) % p
+            den = den * (w + beta * sigma_values[j][sigma_stride * (i - 1)] + gamma) % p
+        if den == 0:
+            raise ZeroDivisionError("No inverse")
+        z.append(z[-1] * num * pow(den, -1, p) % p)
+    return z
+
+
 class SplitMix64:
     def __init__(self, seed: int):
         self.s = seed & MASK64

@@ -34,6 +34,7 @@ __all__ = [
     "FftPrecomputation", "fft_precompute", "fft", "fft_with_precomputation", "fft_with_precomputation_power_of_2",
     "ifft_with_precomputation_power_of_2", "fft_batch", "coset_lde", "coset_ifft", "divide_by_z_h",
     "field_op", "batch_multiplicative_inverse", "batch_to_affine", "affine_summation_best", "affine_multisummation_best", "curve_mul", "points_generate", "kernel_launch_count",
+    "polynomial_mul", "eval_domain", "from_evaluations", "permutation_polynomial",
     "HaloIpaRounds", "blake_hash_usize_to_curve", "blake_hash_base_field_to_curve", "points_to_bytes", "points_from_bytes",
 ]
 
@@ -122,6 +123,8 @@ def lib():
     L.plk_coset_ifft.argtypes = [vp, u64p, u64p, u64p]
     L.plk_divide_by_z_h.argtypes = [vp, u64p, sz, sz, u64p]
     L.plk_fft_dev.argtypes = [vp, vp, sz, sz, C.c_uint, vp, vp]
+    L.plk_permutation_polynomial.argtypes = [C.c_int, sz, C.c_uint, u64p, u64p, sz, u64p, sz, sz, u64p, u64p, u64p, u64p]
+    L.plk_poly_mul.argtypes = [C.c_int, u64p, sz, u64p, sz, u64p, sz, C.POINTER(sz)]
     L.plk_fft_dist_phase_a.argtypes = [vp, vp, vp, sz, sz, C.c_uint, C.c_uint, vp, vp, vp]
     L.plk_fft_dist_phase_b.argtypes = [vp, vp, C.c_uint, C.c_uint, C.c_uint, vp]
     L.plk_field_op.argtypes = [C.c_int, C.c_int, u64p, u64p, u64p, sz]
@@ -623,3 +626,49 @@ def points_from_bytes(curve: int, data):
     st = np.zeros(n, dtype=np.uint8)
     _check(lib().plk_points_decompress(curve, _p8(d), n, _p64(out), _p8(z), _p8(st)))
     return out, z
+
+
+# ------------------------------------------------------------------------------------------------
+# Polynomial helpers that are thin wrappers of the transforms (src/polynomial.rs:135-151, 209-227)
+# ------------------------------------------------------------------------------------------------
+def eval_domain(coeffs, fft_precomputation: "FftPrecomputation") -> np.ndarray:
+    """Polynomial::eval_domain (polynomial.rs:135-143): zero-pad to the domain size and transform."""
+    return fft_with_precomputation(coeffs, fft_precomputation)
+
+
+def from_evaluations(values, fft_precomputation: "FftPrecomputation") -> np.ndarray:
+    """Polynomial::from_evaluations (polynomial.rs:146-151)."""
+    return ifft_with_precomputation_power_of_2(values, fft_precomputation)
+
+
+def polynomial_mul(field: int, a, b) -> np.ndarray:
+    """Polynomial::mul (polynomial.rs:209-227): the un-trimmed IFFT output, 2^log2_ceil(deg a + deg b + 1) coefficients
+    ((1, L) zeros when either operand is the zero polynomial)."""
+    L = FIELD_LIMBS[field]
+    a, b = _u64(a).reshape(-1, L), _u64(b).reshape(-1, L)
+    cap = 1
+    while cap < max(1, a.shape[0] + b.shape[0]):
+        cap <<= 1
+    out = np.zeros((cap, L), dtype=np.uint64)
+    n = C.c_size_t()
+    _check(lib().plk_poly_mul(field, _p64(a), a.shape[0], _p64(b), b.shape[0], _p64(out), cap, C.byref(n)))
+    return out[:n.value].copy()
+
+
+def permutation_polynomial(field: int, subgroup, wire_values, sigma_values, k_is, beta, gamma, num_routed: int = 6,
+                           sigma_stride: int = 8) -> np.ndarray:
+    """permutation_polynomial(degree, subgroup, witness, sigma_values, beta, gamma) (src/plonk_util.rs:233-262).
+    subgroup (n, L); wire_values (n, NUM_WIRES, L) = Witness::wire_values; sigma_values (num_routed, sigma_stride * n, L)
+    (the 8n-point evaluations the reference indexes with 8 * (i - 1)); k_is (num_routed, L); beta, gamma (L,)."""
+    L = FIELD_LIMBS[field]
+    sub = _u64(subgroup).reshape(-1, L)
+    n = sub.shape[0]
+    w = _u64(wire_values)
+    w = w.reshape(n, -1, L)
+    sig = _u64(sigma_values).reshape(num_routed, -1, L)
+    k = _u64(k_is).reshape(num_routed, L)
+    b, g = _u64(beta).reshape(L), _u64(gamma).reshape(L)
+    out = np.zeros((n, L), dtype=np.uint64)
+    _check(lib().plk_permutation_polynomial(field, n, num_routed, _p64(sub), _p64(w), w.shape[1], _p64(sig), sig.shape[1], sigma_stride,
+                                            _p64(k), _p64(b), _p64(g), _p64(out)))
+    return out

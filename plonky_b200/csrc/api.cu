@@ -172,6 +172,131 @@ void launch_batch_inverse(const void* in, void* out, size_t n, int* d_flag, cuda
   PLK_LAUNCHED();
 }
 
+// ---- permutation_polynomial (src/plonk_util.rs:233-262) ---------------------------------------------------------------
+// Z(g^0) = 1, Z(g^i) = Z(g^(i-1)) * prod_j (w_j + beta k_j x + gamma) / prod_j (w_j + beta sigma_j + gamma) over the routed
+// wires j of gate i - 1.  Device: one thread per gate for numerator and denominator, Montgomery's trick for the n
+// divisions, then an exclusive prefix PRODUCT over the ratios (field multiplication is associative and exact, so the
+// scan order cannot change a value).
+struct PermArgs {
+  const void* subgroup;     // n elements
+  const void* wires;        // wire (i, j) at i * wire_stride + j
+  const void* sigma;        // sigma_j at j * sigma_row + sigma_stride * i
+  const void* kis;          // routed shifts k_j
+  const void* beta_gamma;   // beta, gamma
+  unsigned long long n, wire_stride, sigma_row, sigma_stride;
+  unsigned routed;
+};
+template <class P>
+__global__ void perm_ratio_terms_kernel(PermArgs a, void* __restrict__ num, void* __restrict__ den) {
+  typedef Fp<P> F;
+  const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (i + 1 >= a.n) return;                         // gates 0 .. n - 2 feed Z(g^1) .. Z(g^(n-1))
+  const F beta = load_fp<F>(a.beta_gamma, 0), gamma = load_fp<F>(a.beta_gamma, 1);
+  const F bx = F::mul(beta, load_fp<F>(a.subgroup, i));
+  F nu = F::one(), de = F::one();
+  for (unsigned j = 0; j < a.routed; ++j) {
+    const F w = F::add(load_fp<F>(a.wires, i * a.wire_stride + j), gamma);
+    nu = F::mul(nu, F::add(w, F::mul(load_fp<F>(a.kis, j), bx)));                                        // w + beta k_j x + gamma
+    de = F::mul(de, F::add(w, F::mul(beta, load_fp<F>(a.sigma, j * a.sigma_row + a.sigma_stride * i))));   // w + beta sigma + gamma
+  }
+  store_fp<F>(num, i, nu);
+  store_fp<F>(den, i, de);
+}
+constexpr int kScanThreads = 256, kScanPerThread = 4, kScanTile = kScanThreads * kScanPerThread;
+// inclusive product scan of one tile of r = num * den_inv (computed on the fly); tile totals to `totals`
+template <class P>
+__global__ void __launch_bounds__(kScanThreads) perm_tile_scan_kernel(const void* __restrict__ num, const void* __restrict__ den_inv,
+                                                                      unsigned long long m, void* __restrict__ scanned, void* __restrict__ totals) {
+  typedef Fp<P> F;
+  __shared__ uint4 sm[kScanThreads * (F::N / 4)];
+  const unsigned long long base = (unsigned long long)blockIdx.x * kScanTile + (unsigned long long)threadIdx.x * kScanPerThread;
+  F v[kScanPerThread];
+  F run = F::one();
+#pragma unroll
+  for (int e = 0; e < kScanPerThread; ++e) {
+    const unsigned long long i = base + e;
+    const F r = i < m ? F::mul(load_fp<F>(num, i), load_fp<F>(den_inv, i)) : F::one();
+    run = F::mul(run, r);
+    v[e] = run;
+  }
+  // block-wide inclusive scan of the per-thread products (Hillis-Steele in shared memory)
+  store_fp<F>(sm, threadIdx.x, run);
+  __syncthreads();
+  F acc = run;
+  for (unsigned d = 1; d < kScanThreads; d <<= 1) {
+    F other = F::one();
+    if (threadIdx.x >= d) other = load_fp<F>(sm, threadIdx.x - d);
+    __syncthreads();
+    if (threadIdx.x >= d) acc = F::mul(acc, other);
+    store_fp<F>(sm, threadIdx.x, acc);
+    __syncthreads();
+  }
+  const F before = threadIdx.x ? load_fp<F>(sm, threadIdx.x - 1) : F::one();
+#pragma unroll
+  for (int e = 0; e < kScanPerThread; ++e) {
+    const unsigned long long i = base + e;
+    if (i < m) store_fp<F>(scanned, i, F::mul(before, v[e]));
+  }
+  if (threadIdx.x == kScanThreads - 1) store_fp<F>(totals, blockIdx.x, acc);
+}
+// single CTA: exclusive product scan of the tile totals, in place (tiles <= 4096 here: n <= 2^22)
+template <class P>
+__global__ void __launch_bounds__(1024) perm_totals_scan_kernel(void* __restrict__ totals, unsigned tiles) {
+  typedef Fp<P> F;
+  __shared__ uint4 sm[1024 * (F::N / 4)];
+  const unsigned per = (tiles + 1023) / 1024;
+  const unsigned lo = threadIdx.x * per;
+  F run = F::one();
+  for (unsigned i = lo; i < lo + per && i < tiles; ++i) run = F::mul(run, load_fp<F>(totals, i));
+  store_fp<F>(sm, threadIdx.x, run);
+  __syncthreads();
+  F acc = run;
+  for (unsigned d = 1; d < 1024; d <<= 1) {
+    F other = F::one();
+    if (threadIdx.x >= d) other = load_fp<F>(sm, threadIdx.x - d);
+    __syncthreads();
+    if (threadIdx.x >= d) acc = F::mul(acc, other);
+    store_fp<F>(sm, threadIdx.x, acc);
+    __syncthreads();
+  }
+  F before = threadIdx.x ? load_fp<F>(sm, threadIdx.x - 1) : F::one();
+  for (unsigned i = lo; i < lo + per && i < tiles; ++i) {
+    const F t = load_fp<F>(totals, i);
+    store_fp<F>(totals, i, before);
+    before = F::mul(before, t);
+  }
+}
+// out[0] = 1, out[i + 1] = tile prefix * scanned[i]
+template <class P>
+__global__ void perm_finish_kernel(const void* __restrict__ scanned, const void* __restrict__ totals, unsigned long long m, void* __restrict__ out) {
+  typedef Fp<P> F;
+  const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (i == 0) store_fp<F>(out, 0, F::one());
+  if (i >= m) return;
+  store_fp<F>(out, i + 1, F::mul(load_fp<F>(totals, i / kScanTile), load_fp<F>(scanned, i)));
+}
+template <class P>
+void launch_permutation(const PermArgs& a, void* d_num, void* d_den, void* d_inv, void* d_totals, int* d_flag, void* d_out, cudaStream_t st) {
+  typedef Fp<P> F;
+  const size_t m = a.n - 1;                        // ratios
+  if (m == 0) {
+    perm_finish_kernel<P><<<1, 32, 0, st>>>(d_num, d_totals, 0, d_out);
+    PLK_LAUNCHED();
+    return;
+  }
+  perm_ratio_terms_kernel<P><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(a, d_num, d_den);
+  PLK_LAUNCHED();
+  launch_batch_inverse<P>(d_den, d_inv, m, d_flag, st);
+  const unsigned tiles = (unsigned)((m + kScanTile - 1) / kScanTile);
+  perm_tile_scan_kernel<P><<<tiles, kScanThreads, 0, st>>>(d_num, d_inv, m, d_den /* reuse: scanned */, d_totals);
+  PLK_LAUNCHED();
+  perm_totals_scan_kernel<P><<<1, 1024, 0, st>>>(d_totals, tiles);
+  PLK_LAUNCHED();
+  perm_finish_kernel<P><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(d_den, d_totals, m, d_out);
+  PLK_LAUNCHED();
+  (void)sizeof(F);
+}
+
 }  // namespace plk
 
 using namespace plk;
@@ -185,6 +310,9 @@ using namespace plk;
     default: fail(PLK_EINVAL, "unknown field id");                                 \
   }
 
+void plk_launch_field_mul(int field, const void* d_a, const void* d_b, void* d_out, size_t n, cudaStream_t st) {
+  PLK_FIELD_DISPATCH(field, launch_field_op, 2, d_a, d_b, d_out, n, st);
+}
 void plk_launch_field_inverse(int field, const void* d_in, void* d_out, size_t n, cudaStream_t st) {
   PLK_FIELD_DISPATCH(field, launch_field_op, 5, d_in, nullptr, d_out, n, st);
 }
@@ -269,6 +397,40 @@ int plk_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64
     PLK_FIELD_DISPATCH(field, launch_field_op, op, da, b ? db : nullptr, dout, n, st);
     PLK_CUDA(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, st));
     PLK_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+int plk_permutation_polynomial(int field, size_t degree, unsigned num_routed, const uint64_t* subgroup, const uint64_t* wires,
+                               size_t wire_stride, const uint64_t* sigma, size_t sigma_row_len, size_t sigma_stride, const uint64_t* k_is,
+                               const uint64_t* beta, const uint64_t* gamma, uint64_t* out) {
+  return guarded([&] {
+    const int L = plk_field_limbs(field);
+    if (!L) fail(PLK_EINVAL, "unknown field id");
+    if (degree == 0) return;
+    if (!subgroup || !wires || !sigma || !k_is || !beta || !gamma || !out) fail(PLK_EINVAL, "NULL buffer");
+    if (num_routed == 0 || num_routed > wire_stride) fail(PLK_EINVAL, "num_routed must be in 1..wire_stride");
+    if (sigma_stride == 0 || (degree - 1) * sigma_stride >= sigma_row_len + (degree == 1 ? 1 : 0)) fail(PLK_EINVAL, "sigma rows too short for the stride");
+    if (degree > ((size_t)1 << 22)) fail(PLK_EINVAL, "degree above 2^22 is not supported");
+    cudaStream_t st = thread_stream();
+    const size_t eb = (size_t)L * 8, n = degree;
+    DevBuf d_sub(n * eb, st), d_w(n * wire_stride * eb, st), d_sig((size_t)num_routed * sigma_row_len * eb, st), d_k(num_routed * eb, st), d_bg(2 * eb, st);
+    DevBuf d_num(n * eb, st), d_den(n * eb, st), d_inv(n * eb, st), d_tot((n / kScanTile + 2) * eb, st), d_out(n * eb, st), d_flag(16, st);
+    PLK_CUDA(cudaMemcpyAsync(d_sub.p, subgroup, n * eb, cudaMemcpyHostToDevice, st));
+    PLK_CUDA(cudaMemcpyAsync(d_w.p, wires, n * wire_stride * eb, cudaMemcpyHostToDevice, st));
+    PLK_CUDA(cudaMemcpyAsync(d_sig.p, sigma, (size_t)num_routed * sigma_row_len * eb, cudaMemcpyHostToDevice, st));
+    PLK_CUDA(cudaMemcpyAsync(d_k.p, k_is, num_routed * eb, cudaMemcpyHostToDevice, st));
+    PLK_CUDA(cudaMemcpyAsync(d_bg.p, beta, eb, cudaMemcpyHostToDevice, st));
+    PLK_CUDA(cudaMemcpyAsync((char*)d_bg.p + eb, gamma, eb, cudaMemcpyHostToDevice, st));
+    PLK_CUDA(cudaMemsetAsync(d_flag.p, 0, sizeof(int), st));
+    PermArgs a;
+    a.subgroup = d_sub.p; a.wires = d_w.p; a.sigma = d_sig.p; a.kis = d_k.p; a.beta_gamma = d_bg.p;
+    a.n = n; a.wire_stride = wire_stride; a.sigma_row = sigma_row_len; a.sigma_stride = sigma_stride; a.routed = num_routed;
+    PLK_FIELD_DISPATCH(field, launch_permutation, a, d_num.p, d_den.p, d_inv.p, d_tot.p, d_flag.as<int>(), d_out.p, st);
+    int flag = 0;
+    PLK_CUDA(cudaMemcpyAsync(&flag, d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PLK_CUDA(cudaMemcpyAsync(out, d_out.p, n * eb, cudaMemcpyDeviceToHost, st));
+    PLK_CUDA(cudaStreamSynchronize(st));
+    if (flag) fail(PLK_EZERO, "No inverse");          // a zero denominator: the reference's `/` panics (field.rs Div)
   });
 }
 

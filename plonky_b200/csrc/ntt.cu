@@ -1,8 +1,13 @@
 // C ABI of the NTT (include/plonky_b200.h); kernels live in ntt_kernels.cuh, one translation unit per field.
+#include <map>
+#include <mutex>
+#include <tuple>
 #include "ntt_plan.h"
 #include "field_constants.cuh"
 
 using namespace plk;
+
+void plk_launch_field_mul(int field, const void* d_a, const void* d_b, void* d_out, size_t n, cudaStream_t st);   // api.cu
 
 namespace plk {
 const NttOps* ntt_ops_tweedledee_base();
@@ -178,6 +183,73 @@ int plk_divide_by_z_h(const plk_fft_plan* p, const uint64_t* coeffs, size_t n_in
     ops_for(pl->field)->run(pl, d_mid, pl->n, pl->n, d_out, 1, true, &bwd, st);
     PLK_CUDA(cudaMemcpyAsync(out, d_out, pl->n * eb, cudaMemcpyDeviceToHost, st));
     PLK_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+/* Polynomial::mul (src/polynomial.rs:209-227): both operands zero-padded to deg a + deg b + 1, FFT of the size
+ * 2^log2_ceil(that), pointwise product, IFFT -- here two fused-padding transforms, one product kernel and the inverse
+ * transform without leaving the device.  The reference rebuilds the FftPrecomputation on every call (:217); the plans
+ * are cached per (field, log size, device) instead. */
+int plk_poly_mul(int field, const uint64_t* a, size_t na, const uint64_t* b, size_t nb, uint64_t* out, size_t out_cap, size_t* out_len) {
+  return guarded([&] {
+    const int L = plk_field_limbs(field);
+    if (!L) fail(PLK_EINVAL, "unknown field id");
+    if ((na && !a) || (nb && !b) || !out || !out_len) fail(PLK_EINVAL, "NULL buffer");
+    auto degree_plus_one = [L](const uint64_t* p, size_t n) {          // Polynomial::degree after trim (:105-118)
+      while (n > 0) {
+        bool zero = true;
+        for (int j = 0; j < L; ++j) zero = zero && p[(n - 1) * L + j] == 0;
+        if (!zero) break;
+        --n;
+      }
+      return n;
+    };
+    const size_t la = degree_plus_one(a, na), lb = degree_plus_one(b, nb);
+    if (la == 0 || lb == 0) {                                          // is_zero: Self::zero(1)
+      if (out_cap < 1) fail(PLK_ESIZE, "output buffer too small");
+      for (int j = 0; j < L; ++j) out[j] = 0;
+      *out_len = 1;
+      return;
+    }
+    const size_t size = la + lb - 1;                                   // a_deg + b_deg + 1
+    const int ta = field_two_adicity(field);
+    const int lg = log2_ceil(size);
+    if (lg > ta) fail(PLK_ETOOBIG, "log2(size) exceeds TWO_ADICITY");
+    const size_t n = (size_t)1 << lg;
+    if (out_cap < n) fail(PLK_ESIZE, "output buffer too small (needs 2^log2_ceil(deg a + deg b + 1) elements)");
+    // plan cache
+    static std::mutex mu;
+    static std::map<std::tuple<int, int, int>, plk_fft_plan*> cache;
+    int dev = 0;
+    PLK_CUDA(cudaGetDevice(&dev));
+    plk_fft_plan* pl = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      auto key = std::make_tuple(field, lg, dev);
+      auto it = cache.find(key);
+      if (it == cache.end()) {
+        plk_fft_plan* fresh = nullptr;
+        const int rc = plk_fft_precompute(field, n, &fresh);
+        if (rc != PLK_OK) fail(rc, plk_last_error_message());
+        it = cache.emplace(key, fresh).first;
+      }
+      pl = it->second;
+    }
+    cudaStream_t st = thread_stream();
+    const size_t eb = pl->elem_bytes;
+    char* d_in = reinterpret_cast<char*>(thread_scratch(0, (la + lb) * eb));
+    char* d_ev = reinterpret_cast<char*>(thread_scratch(1, 2 * n * eb));
+    char* d_out = reinterpret_cast<char*>(thread_scratch(2, n * eb));
+    PLK_CUDA(cudaMemcpyAsync(d_in, a, la * eb, cudaMemcpyHostToDevice, st));
+    PLK_CUDA(cudaMemcpyAsync(d_in + la * eb, b, lb * eb, cudaMemcpyHostToDevice, st));
+    const FusedOps none;
+    ops_for(field)->run(pl, d_in, la, la, d_ev, 1, false, &none, st);
+    ops_for(field)->run(pl, d_in + la * eb, lb, lb, d_ev + n * eb, 1, false, &none, st);
+    plk_launch_field_mul(field, d_ev, d_ev + n * eb, d_ev, n, st);
+    ops_for(field)->run(pl, d_ev, n, n, d_out, 1, true, &none, st);
+    PLK_CUDA(cudaMemcpyAsync(out, d_out, n * eb, cudaMemcpyDeviceToHost, st));
+    PLK_CUDA(cudaStreamSynchronize(st));
+    *out_len = n;
   });
 }
 

@@ -8,7 +8,7 @@ import pytest
 
 import plonky_oracle as po
 import plonky_b200 as pk
-from helpers import ints_to_limbs, limbs_to_ints, mont_array, canon_list, points_to_array
+from helpers import ints_to_limbs, limbs_to_ints, mont_array, canon_list, points_to_array, rand_scalars
 
 pytestmark = pytest.mark.gpu
 
@@ -154,3 +154,40 @@ def test_invalid_arguments_return_errors_not_crashes():
         pk.msm_execute(pre, np.zeros((3, 4), dtype=np.uint64))
     with pytest.raises(pk.PlonkyPanic):
         pk.msm_parallel(c.cid, np.zeros((3, 4), dtype=np.uint64), proj(c, [c.gen, c.gen])[0], 8)
+
+
+@pytest.mark.parametrize("name", list(po.FIELDS))
+def test_polynomial_mul(name):
+    """Polynomial::mul (polynomial.rs:209-227) against the schoolbook product, including zero operands, trailing zero
+    coefficients (degree < length) and the un-trimmed power-of-two output length."""
+    f = po.FIELDS[name]
+    cases = [([1], [1]), ([0], [5, 6]), ([], [1]), ([3, 0, 0], [0, 0, 7, 0]), (rand_scalars(f, 1, 5), rand_scalars(f, 2, 7)),
+             (rand_scalars(f, 3, 200), rand_scalars(f, 4, 313)), ([f.p - 1] * 33, [f.p - 1] * 32), (rand_scalars(f, 5, 1024) + [0, 0], [2])]
+    for a, b in cases:
+        got = pk.polynomial_mul(f.fid, mont_array(f, a) if a else np.zeros((0, f.limbs), dtype=np.uint64),
+                                mont_array(f, b) if b else np.zeros((0, f.limbs), dtype=np.uint64))
+        assert canon_list(f, got) == po.poly_mul(f, a, b)
+
+
+@pytest.mark.parametrize("name,n", [("TweedledeeBase", 1), ("TweedledeeBase", 2), ("TweedledumBase", 700), ("TweedledumBase", 4096), ("Bls12377Scalar", 1500)])
+def test_permutation_polynomial(name, n):
+    """permutation_polynomial (plonk_util.rs:233-262): Z on the subgroup, 6 routed of 9 wires, sigma read with stride 8,
+    against the sequential big-integer restatement; a zero denominator panics like the reference's division."""
+    f = po.FIELDS[name]
+    routed, wires, stride = 6, 9, 8
+    sub = rand_scalars(f, 41, n)
+    w = [rand_scalars(f, 100 + i, wires) for i in range(n)]
+    sig = [rand_scalars(f, 5000 + j, stride * n) for j in range(routed)]
+    k_is = rand_scalars(f, 77, routed)
+    beta, gamma = rand_scalars(f, 78, 2)
+    want = po.permutation_polynomial(f, sub, w, sig, k_is, beta, gamma)
+    W = np.stack([mont_array(f, row) for row in w]) if n else np.zeros((0, wires, f.limbs), dtype=np.uint64)
+    S = np.stack([mont_array(f, row) for row in sig])
+    got = pk.permutation_polynomial(f.fid, mont_array(f, sub), W, S, mont_array(f, k_is), mont_array(f, [beta])[0], mont_array(f, [gamma])[0])
+    assert canon_list(f, got) == want
+    if n >= 700:
+        # force w + beta sigma + gamma == 0 at gate 5, wire 2
+        w[5][2] = (-(beta * sig[2][stride * 5] + gamma)) % f.p
+        W = np.stack([mont_array(f, row) for row in w])
+        with pytest.raises(pk.PlonkyPanic):
+            pk.permutation_polynomial(f.fid, mont_array(f, sub), W, S, mont_array(f, k_is), mont_array(f, [beta])[0], mont_array(f, [gamma])[0])
