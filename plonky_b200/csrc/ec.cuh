@@ -24,6 +24,8 @@ namespace plk {
 // inlined product: its many warps share every fetched line.)
 template <class F>
 PLK_HD_NOINLINE F fp_mul_call(const F a, const F b) { return F::mul(a, b); }
+template <class F>
+PLK_HD_NOINLINE F fp_sqr_call(const F a) { return F::sqr(a); }
 
 template <class C>
 struct Affine {
@@ -66,13 +68,13 @@ struct XYZZ {
   PLK_HD_NOINLINE static XYZZ dbl(const XYZZ& p) {
     if (p.is_identity() || p.y.is_zero()) return identity();
     F u = F::dbl(p.y);
-    F v = fp_mul_call<F>(u, u);
+    F v = fp_sqr_call<F>(u);
     F w = fp_mul_call<F>(u, v);
     F s = fp_mul_call<F>(p.x, v);
-    F xx = fp_mul_call<F>(p.x, p.x);
+    F xx = fp_sqr_call<F>(p.x);
     F m = F::add(F::dbl(xx), xx);           // a = 0
     XYZZ r;
-    r.x = F::sub(fp_mul_call<F>(m, m), F::dbl(s));
+    r.x = F::sub(fp_sqr_call<F>(m), F::dbl(s));
     r.y = F::sub(fp_mul_call<F>(m, F::sub(s, r.x)), fp_mul_call<F>(w, p.y));
     r.zz = fp_mul_call<F>(v, p.zz);
     r.zzz = fp_mul_call<F>(w, p.zzz);
@@ -114,11 +116,11 @@ struct XYZZ {
       if (r.is_zero()) return dbl(a);
       return identity();
     }
-    F pp = fp_mul_call<F>(p, p);
+    F pp = fp_sqr_call<F>(p);
     F ppp = fp_mul_call<F>(p, pp);
     F qq = fp_mul_call<F>(u1, pp);
     XYZZ o;
-    o.x = F::sub(F::sub(fp_mul_call<F>(r, r), ppp), F::dbl(qq));
+    o.x = F::sub(F::sub(fp_sqr_call<F>(r), ppp), F::dbl(qq));
     o.y = F::sub(fp_mul_call<F>(r, F::sub(qq, o.x)), fp_mul_call<F>(s1, ppp));
     o.zz = fp_mul_call<F>(fp_mul_call<F>(a.zz, b.zz), pp);
     o.zzz = fp_mul_call<F>(fp_mul_call<F>(a.zzz, b.zzz), ppp);

@@ -240,7 +240,86 @@ struct Fp {
     t.l[N - 1] = ptx::addc(E[N - 1], O[N - 2]);
     return reduce_once(t);
   }
-  PLK_HD static Fp sqr(const Fp& a) { return mul(a, a); }   // monty.rs:109-160 (same value)
+  // Row i of the upper-triangular squaring: like mad_chain, but operand limbs t = start + j below `from` are
+  // compile-time zeros (no product; a CIN chain still has to carry through them).
+  template <bool CIN, bool COUT, int LEN>
+  PLK_HD static void mad_chain_from(uint32_t (&acc)[LEN], const uint32_t (&x)[N], int start, int from, uint32_t y) {
+    bool started = CIN;
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+      const bool last = !(j + 2 < N || COUT);
+      if (start + j < from) {
+        if (started) {
+          acc[j] = ptx::addc_cc(acc[j], 0);
+          acc[j + 1] = last ? ptx::addc(acc[j + 1], 0) : ptx::addc_cc(acc[j + 1], 0);
+        }
+      } else {
+        acc[j] = started ? ptx::madc_lo_cc(x[start + j], y, acc[j]) : ptx::mad_lo_cc(x[start + j], y, acc[j]);
+        acc[j + 1] = last ? ptx::madc_hi(x[start + j], y, acc[j + 1]) : ptx::madc_hi_cc(x[start + j], y, acc[j + 1]);
+        started = true;
+      }
+    }
+    if (COUT && started) acc[N] = ptx::addc(acc[N], 0);
+  }
+  // monty.rs:109-160 (same value as mul(a, a)).  PLK_SQR_DEDICATED: upper-triangular rows -- row i multiplies a_i with
+  // a_i and with the DOUBLED limbs above it (36 instead of 64 limb products for N = 8), same interleaved reduction.
+  // Doubling limbs i+1.. as a number: d_t = (a_t << 1) | (a_(t-1) >> 31), except that limb i + 1 takes no bit from a_i.
+#ifndef PLK_SQR_DEDICATED
+#define PLK_SQR_DEDICATED 1
+#endif
+  PLK_HD static Fp sqr(const Fp& a) {
+#if PLK_SQR_DEDICATED
+    static_assert(N % 2 == 0, "even limb count");
+    uint32_t d[N];                      // 2a, limb-wise (2a < 2^(32N) for every modulus here)
+    d[0] = a.l[0] << 1;
+#pragma unroll
+    for (int t = 1; t < N; ++t) d[t] = (a.l[t] << 1) | (a.l[t - 1] >> 31);
+    uint32_t E[N + 1], O[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { E[i] = 0; O[i] = 0; }
+    E[N] = 0;
+    uint32_t pend = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      uint32_t x[N];                    // operand limbs of row i: 0 below i, a_i, then the doubled limbs above
+#pragma unroll
+      for (int t = 0; t < N; ++t) x[t] = t < i ? 0u : (t == i ? a.l[i] : (t == i + 1 ? (d[t] & 0xfffffffeu) : d[t]));
+      if (i == 0) {
+        mad_chain_from<false, false, N>(O, x, 1, i, a.l[i]);
+      } else {
+        E[0] = ptx::add_cc(E[0], pend);
+        mad_chain_from<true, false, N>(O, x, 1, i, a.l[i]);
+      }
+      mad_chain_from<false, true, N + 1>(E, x, 0, i, a.l[i]);
+#ifdef __CUDA_ARCH__
+      uint32_t m = E[0] * kMontMu32;
+#else
+      uint32_t m = E[0] * P::MU32;
+#endif
+      mad_chain_mod<true, N + 1>(E, 0, m);
+      mad_chain_mod<false, N>(O, 1, m);
+      pend = E[1];
+      uint32_t nE[N + 1], nO[N];
+#pragma unroll
+      for (int k = 0; k < N; ++k) nE[k] = O[k];
+      nE[N] = 0;
+#pragma unroll
+      for (int k = 0; k + 2 <= N; ++k) nO[k] = E[k + 2];
+      nO[N - 1] = 0;
+#pragma unroll
+      for (int k = 0; k < N; ++k) { E[k] = nE[k]; O[k] = nO[k]; }
+      E[N] = 0;
+    }
+    Fp t;
+    t.l[0] = ptx::add_cc(E[0], pend);
+#pragma unroll
+    for (int k = 1; k < N - 1; ++k) t.l[k] = ptx::addc_cc(E[k], O[k - 1]);
+    t.l[N - 1] = ptx::addc(E[N - 1], O[N - 2]);
+    return reduce_once(t);
+#else
+    return mul(a, a);
+#endif
+  }
 
   PLK_HD Fp operator+(const Fp& o) const { return add(*this, o); }
   PLK_HD Fp operator-(const Fp& o) const { return sub(*this, o); }

@@ -1,12 +1,12 @@
 // Throughput micro-benchmark of the Montgomery product (tuning tool, not part of the library):
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Iplonky_b200/csrc tools/bench_mul.cu -o /tmp/bench_mul
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Iplonky_b200/csrc [-DPLK_SQR_DEDICATED=0|1] tools/bench_mul.cu -o /tmp/bench_mul
 // Every thread runs 4 independent chains of dependent products (like the 4-deep ILP of a mixed addition); prints
 // products/s over the whole GPU and the checksum (identical across variants = same values).
 #include <cstdio>
 #include <cuda_runtime.h>
 #include "fp.cuh"
 using namespace plk;
-template <class P>
+template <class P, bool SQR>
 __global__ void __launch_bounds__(128) mul_loop(const uint32_t* seed, int iters, uint32_t* out) {
   typedef Fp<P> F;
   F a[4], b;
@@ -18,13 +18,13 @@ __global__ void __launch_bounds__(128) mul_loop(const uint32_t* seed, int iters,
   for (int c = 0; c < 4; ++c) a[c].l[F::N - 1] &= 0x0fffffffu;
   for (int i = 0; i < iters; ++i) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) a[c] = F::mul(a[c], b);
+    for (int c = 0; c < 4; ++c) a[c] = SQR ? F::sqr(a[c]) : F::mul(a[c], b);
   }
   uint32_t acc = 0;
   for (int c = 0; c < 4; ++c) for (int k = 0; k < F::N; ++k) acc ^= a[c].l[k];
   out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
-template <class P>
+template <class P, bool SQR>
 void run(const char* name) {
   const int blocks = 148 * 4, threads = 128, iters = 2000;
   uint32_t h_seed[32];
@@ -36,12 +36,12 @@ void run(const char* name) {
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  mul_loop<P><<<blocks, threads>>>(d_seed, 10, d_out);
+  mul_loop<P, SQR><<<blocks, threads>>>(d_seed, 10, d_out);
   cudaDeviceSynchronize();
   float best = 1e9f;
   for (int rep = 0; rep < 5; ++rep) {
     cudaEventRecord(e0);
-    mul_loop<P><<<blocks, threads>>>(d_seed, iters, d_out);
+    mul_loop<P, SQR><<<blocks, threads>>>(d_seed, iters, d_out);
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
     float ms;
@@ -57,7 +57,9 @@ void run(const char* name) {
          cudaGetErrorString(cudaGetLastError()));
 }
 int main() {
-  run<TweedledeeBaseParams>("TweedledeeBase");
-  run<Bls12377BaseParams>("Bls12377Base");
+  run<TweedledeeBaseParams, false>("TweedledeeBase mul");
+  run<TweedledeeBaseParams, true>("TweedledeeBase sqr");
+  run<Bls12377BaseParams, false>("Bls12377Base mul");
+  run<Bls12377BaseParams, true>("Bls12377Base sqr");
   return 0;
 }
