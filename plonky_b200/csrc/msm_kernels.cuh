@@ -35,6 +35,25 @@ namespace plk {
 // signed window recoding of a canonical scalar; calls f(window, bucket_index, negative)
 template <class SF, class Fn>
 __device__ __forceinline__ void for_each_digit(const SF& canon, const MsmGeom& g, Fn&& f) {
+  if (g.c == 16 && !g.variable && g.nwin <= 2 * SF::N) {
+    // 16-bit windows are the two halves of each limb: fully unrolled, no dynamic limb indexing (the generic loop
+    // below costs ~1500 instructions per scalar, most of them address arithmetic around canon.l[limb])
+    unsigned carry = 0;
+#pragma unroll
+    for (int j = 0; j < 2 * SF::N; ++j) {
+      if (j < g.nwin) {
+        unsigned raw = ((canon.l[j >> 1] >> ((j & 1) * 16)) & 0xffffu) + carry;
+        carry = 0;
+        if (raw > 0x8000u) {
+          carry = 1;
+          if (raw != 0x10000u) f(j, 0x10000u - raw - 1, true);
+        } else if (raw != 0) {
+          f(j, raw - 1, false);
+        }
+      }
+    }
+    return;
+  }
   unsigned carry = 0;
   const unsigned full = 1u << g.c, halfw = 1u << (g.c - 1), mask = full - 1;
   for (int j = 0; j < g.nwin; ++j) {
