@@ -228,7 +228,7 @@ struct QuadXYZZ {
     for (int i = 0; i < 4; ++i) all[i] = load_fp<F>(buf, i);
     c.phase ^= 1;
   }
-  static __device__ __noinline__ P dbl(const P& a, Ctx& c) {
+  static __device__ __forceinline__ P dbl(const P& a, Ctx& c) {
     if (a.is_identity() || a.y.is_zero()) return P::identity();
     const int ql = c.ql;
     F g[4];
@@ -246,7 +246,7 @@ struct QuadXYZZ {
     r.y = F::sub(g[2], g[0]);
     return r;
   }
-  static __device__ __noinline__ P add(const P& a, const P& b, Ctx& c) {
+  static __device__ __forceinline__ P add(const P& a, const P& b, Ctx& c) {
     if (a.is_identity()) return b;
     if (b.is_identity()) return a;
     const int ql = c.ql;
