@@ -280,14 +280,16 @@ def run_ours(args):
         step(i)
     barrier()
     launches0 = pk.kernel_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]      # one event per step boundary (median + min)
+    marks[0].record()
     for i in range(K):
         step(i)
-    ev1.record()
+        marks[i + 1].record()
     barrier()
     launches = pk.kernel_launch_count() - launches0
-    ms_step = max_over_ranks(ev0.elapsed_time(ev1) / K)
+    ms_step = max_over_ranks(marks[0].elapsed_time(marks[K]) / K)
+    per_step = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(K))
+    step_stats = {"median": per_step[K // 2], "min": per_step[0], "max": per_step[-1]}
     value = world * n / (ms_step * 1e-3)
 
     # ---- per-kernel times (same inputs, same process, right after the timed steps) ----
@@ -351,7 +353,7 @@ def run_ours(args):
 
     line = {
         "metric": "msm_scalar_muls_per_sec", "value": value, "unit": "scalar-muls/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if args.total_terms else "weak", "vs_baseline": None,
+        "ms_per_step": ms_step, "ms_per_step_stats_rank0": step_stats, "higher_is_better": True, "scaling": "strong" if args.total_terms else "weak", "vs_baseline": None,
         "dtype": "u64x6 (Montgomery, 377-bit base field)" if curve == 2 else "u64x4 (Montgomery, 255-bit)", "data": "synthetic",
         "config": {"workload": f"{curve_name} G1 MSM, {n} terms per GPU, fixed-base table (msm_precompute once, execute timed)",
                    "terms_per_gpu": n, "total_terms": world * n, "window_passed": 11, "generators": ("pedersen_g = blake_hash_usize_to_curve(i), derived on device (hash_to_curve.rs:53-76)" if args.generators == "reference" else "synthetic [k_i] G"), "precompute_ms_untimed": precompute_ms,

@@ -105,15 +105,20 @@ def test_device_point_codec(name):
 
 
 @pytest.mark.gpu
-def test_msm_over_reference_generators():
-    """pedersen_hash over the reference's own generator set (blake_hash_usize_to_curve(0..n)), against the oracle MSM."""
+@pytest.mark.parametrize("n,w", [(256, 11), (4096, 8)])
+def test_msm_over_reference_generators(n, w):
+    """pedersen_hash over the reference's own generator set (blake_hash_usize_to_curve(0..n), circuit_builder.rs:1127)
+    against the restatement of msm_execute_parallel -- BASELINE config 1's size with the prover's window (11) and w = 8,
+    edge scalars (0, 1, q - 1, 2^k) included."""
     import plonky_b200 as pk
     import ref_port as rp
     curve = po.TWEEDLEDEE
-    n = 256
+    q = curve.scalar.p
     g = pk.blake_hash_usize_to_curve(curve.cid, 0, n)
-    scalars = mont_array(curve.scalar, rand_scalars(curve.scalar, 31, n))
-    want_xy, want_zero = rp.MsmTable(curve.cid, g, None, 11).execute(scalars, parallel=True)
-    pre = pk.msm_precompute_affine(curve.cid, g, 11)
+    vals = rand_scalars(curve.scalar, 31, n)
+    vals[:6] = [0, 1, q - 1, 1 << 17, (1 << 254) % q, q - 2]
+    scalars = mont_array(curve.scalar, vals)
+    want_xy, want_zero = rp.MsmTable(curve.cid, g, None, w).execute(scalars, parallel=True)
+    pre = pk.msm_precompute_affine(curve.cid, g, w)
     out, oz = pk.pedersen_hash(scalars, pre)
     assert oz == want_zero and np.array_equal(out[:2], want_xy)

@@ -214,3 +214,51 @@ def test_device_round_invariant_2p12():
     ip1 = sum(x * y for x, y in zip(canon_list(sf, a2), canon_list(sf, b2))) % sf.p
     cl, cr = canon_list(sf, ipl.reshape(1, -1))[0], canon_list(sf, ipr.reshape(1, -1))[0]
     assert ip1 == (ip0 + u * u * cl + u_inv * u_inv * cr) % sf.p
+
+
+@pytest.mark.gpu
+def test_ipa_and_generators_from_concurrent_host_threads():
+    """The reference runs this path from rayon workers: four host threads, each with its own IPA state against ONE
+    shared table (plus a generator derivation), must reproduce the single-threaded results."""
+    import threading
+    import plonky_b200 as pk
+    curve = po.TWEEDLEDEE
+    sf = curve.scalar
+    n = 256
+    G = pk.blake_hash_usize_to_curve(curve.cid, 0, n)
+    pre = pk.msm_precompute_affine(curve.cid, G, 11)
+    jobs = [(mont_array(sf, rand_scalars(sf, 300 + t, n)), mont_array(sf, rand_scalars(sf, 400 + t, n))) for t in range(4)]
+
+    def run(A, B):
+        st = pk.HaloIpaRounds(curve.cid, A, B, precomputation=pre)
+        trace = []
+        rnd = 0
+        while len(st) > 1:
+            (l, lz), (r, rz), ipl, ipr = st.round_lr()
+            trace += [l.copy(), r.copy(), ipl.copy(), ipr.copy()]
+            u, u_inv = challenge(curve, 900 + rnd)
+            st.fold(mont_array(sf, [u])[0], mont_array(sf, [u_inv])[0])
+            rnd += 1
+        trace += list(st.read())
+        trace.append(pk.blake_hash_usize_to_curve(curve.cid, 1000, 8))
+        return trace
+
+    want = [run(A, B) for A, B in jobs]
+    got = [None] * len(jobs)
+    errors = []
+
+    def work(i):
+        try:
+            got[i] = run(*jobs[i])
+        except Exception as e:      # surfaced below
+            errors.append(e)
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    for w, g in zip(want, got):
+        assert len(w) == len(g)
+        for x, y in zip(w, g):
+            assert np.array_equal(x, y)
