@@ -123,14 +123,18 @@ void run_batch(plk_msm_table* t, const char* d_scalars, size_t k, char* d_out_xy
   {
     std::lock_guard<std::mutex> lk(t->mu);
     if (!t->fork_ev) {
+      if (const char* e = getenv("PLK_MSM_SIDE_STREAMS")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= plk_msm_table::kSideStreamsMax) t->side_streams = v;
+      }
       PLK_CUDA(cudaEventCreateWithFlags(&t->fork_ev, cudaEventDisableTiming));
-      for (int i = 0; i < plk_msm_table::kSideStreams; ++i) {
+      for (int i = 0; i < t->side_streams; ++i) {
         PLK_CUDA(cudaStreamCreateWithFlags(&t->side[i], cudaStreamNonBlocking));
         PLK_CUDA(cudaEventCreateWithFlags(&t->join_ev[i], cudaEventDisableTiming));
       }
     }
   }
-  const int S = plk_msm_table::kSideStreams;
+  const int S = t->side_streams;
   PLK_CUDA(cudaEventRecord(t->fork_ev, st));
   for (int i = 0; i < S && (size_t)i < k; ++i) PLK_CUDA(cudaStreamWaitEvent(t->side[i], t->fork_ev, 0));
   for (size_t j = 0; j < k; ++j)
