@@ -40,6 +40,30 @@ def test_no_cpu_fallback():
         pk.field_op(pk.TWEEDLEDEE_BASE, "mul", np.ones((2, 4), dtype=np.uint64), np.ones((2, 4), dtype=np.uint64))
     with pytest.raises((pk.CudaError, ValueError, pk.PlonkyPanic)):
         pk.msm_precompute_affine(pk.TWEEDLEDEE, np.ones((2, 2, 4), dtype=np.uint64), 8)
+    # the rows added next to the path: IPA rounds, generator derivation, point codec, polynomial helpers
+    one = np.ones((2, 4), dtype=np.uint64)
+    with pytest.raises((pk.CudaError, ValueError, pk.PlonkyPanic)):
+        pk.HaloIpaRounds(pk.TWEEDLEDEE, one, one, np.ones((2, 2, 4), dtype=np.uint64))
+    with pytest.raises((pk.CudaError, ValueError, pk.PlonkyPanic)):
+        pk.blake_hash_usize_to_curve(pk.TWEEDLEDEE, 0, 4)
+    with pytest.raises((pk.CudaError, ValueError, pk.PlonkyPanic)):
+        pk.points_to_bytes(pk.TWEEDLEDEE, np.ones((2, 2, 4), dtype=np.uint64))
+    with pytest.raises((pk.CudaError, ValueError, pk.PlonkyPanic)):
+        pk.polynomial_mul(pk.TWEEDLEDEE_BASE, one, one)
+    with pytest.raises((pk.CudaError, ValueError, pk.PlonkyPanic)):
+        pk.permutation_polynomial(pk.TWEEDLEDEE_BASE, one, np.ones((2, 9, 4), dtype=np.uint64), np.ones((6, 16, 4), dtype=np.uint64),
+                                  np.ones((6, 4), dtype=np.uint64), one[0], one[0])
+
+
+def test_host_side_checks_of_the_new_rows():
+    """Argument checks that mirror the reference's asserts run before any device work."""
+    one = np.ones((4, 4), dtype=np.uint64)
+    with pytest.raises(pk.PlonkyPanic):          # debug_assert_eq!(halo_b.len(), n), halo.rs:68
+        pk.HaloIpaRounds(pk.TWEEDLEDEE, one, one[:2], np.ones((4, 2, 4), dtype=np.uint64))
+    with pytest.raises(ValueError):              # unknown curve id
+        pk.blake_hash_usize_to_curve(7, 0, 1)
+    assert pk.lib().plk_point_compressed_bytes(pk.TWEEDLEDEE) == 33 and pk.lib().plk_point_compressed_bytes(pk.BLS12_377) == 49
+    assert pk.lib().plk_point_compressed_bytes(9) == 0
 
 
 def test_product_never_imports_the_oracle():
