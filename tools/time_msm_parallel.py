@@ -5,7 +5,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import plonky_b200 as pk
 
-for logn in (10, 12, 15, 18, 20):
+for logn in (10, 12, 15, 18):
     n = 1 << logn
     xy = pk.points_generate(pk.TWEEDLEDEE, 5, n)
     xyz = np.zeros((n, 3, 4), dtype=np.uint64)
