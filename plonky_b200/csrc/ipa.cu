@@ -1,5 +1,6 @@
 // C ABI of the device-resident Halo IPA rounds (include/plonky_b200.h, section "Halo inner-product argument").
 #include <memory>
+#include <string.h>
 #include "ipa_kernels.cuh"
 #include "msm_plan.h"
 
@@ -137,13 +138,16 @@ int plk_ipa_round_lr(plk_ipa_state* s, uint64_t* out_l_xyz, uint8_t* out_l_zero,
       msm_variable_dev(s->curve, g, a + half * 32, half, d_r, d_flags + 8, st);        // <a_hi, G_lo>  (halo.rs:91)
     }
     ipa_ops_for(s->curve)->inner_products(s->a.p, s->b.p, half, s->partials.p, d_ip, st);
-    uint8_t flags[16];
-    PLK_CUDA(cudaMemcpyAsync(out_l_xyz, d_l, xyz, cudaMemcpyDeviceToHost, st));
-    PLK_CUDA(cudaMemcpyAsync(out_r_xyz, d_r, xyz, cudaMemcpyDeviceToHost, st));
-    PLK_CUDA(cudaMemcpyAsync(flags, d_flags, 16, cudaMemcpyDeviceToHost, st));
-    PLK_CUDA(cudaMemcpyAsync(out_ip_l, d_ip, 32, cudaMemcpyDeviceToHost, st));
-    PLK_CUDA(cudaMemcpyAsync(out_ip_r, d_ip + 32, 32, cudaMemcpyDeviceToHost, st));
+    // the io block is contiguous (L | R | flags | inner products): one device-to-host copy per round
+    const size_t io_bytes = 2 * xyz + 16 + 64;
+    uint8_t host_io[2 * 3 * 6 * 8 + 16 + 64];
+    PLK_CUDA(cudaMemcpyAsync(host_io, io, io_bytes, cudaMemcpyDeviceToHost, st));
     PLK_CUDA(cudaStreamSynchronize(st));
+    memcpy(out_l_xyz, host_io, xyz);
+    memcpy(out_r_xyz, host_io + xyz, xyz);
+    const uint8_t* flags = host_io + 2 * xyz;
+    memcpy(out_ip_l, host_io + 2 * xyz + 16, 32);
+    memcpy(out_ip_r, host_io + 2 * xyz + 48, 32);
     *out_l_zero = flags[0];
     *out_r_zero = s->table ? flags[1] : flags[8];
   });
@@ -156,8 +160,10 @@ int plk_ipa_fold(plk_ipa_state* s, const uint64_t* u, const uint64_t* u_inv) {
     cudaStream_t st = thread_stream();
     const size_t half = s->n / 2;
     char* d_uu = s->io.as<char>() + 512;
-    PLK_CUDA(cudaMemcpyAsync(d_uu, u, 32, cudaMemcpyHostToDevice, st));
-    PLK_CUDA(cudaMemcpyAsync(d_uu + 32, u_inv, 32, cudaMemcpyHostToDevice, st));
+    uint64_t host_uu[8];
+    memcpy(host_uu, u, 32);
+    memcpy(host_uu + 4, u_inv, 32);
+    PLK_CUDA(cudaMemcpyAsync(d_uu, host_uu, 64, cudaMemcpyHostToDevice, st));
     ipa_ops_for(s->curve)->fold(s->a.p, s->b.p, s->table ? nullptr : s->g.p, half, d_uu, st);
     if (s->table) ipa_ops_for(s->curve)->update_coef(s->coef.p, s->n0, s->n, d_uu, st);
     PLK_CUDA(cudaStreamSynchronize(st));     // u / u_inv are the caller's stack memory
