@@ -16,7 +16,7 @@ namespace plk {
 
 template <int N>
 struct CodecConsts {
-  uint32_t qr_exp[N];     // (p - 1) / 2        Euler's criterion, field.rs:382
+  uint32_t qr_exp[N];     // (p - 1) / 2        Euler's criterion, field.rs:382 (kept for reference; the kernels test a^T instead)
   uint32_t w_exp[N];      // (T - 1) / 2        field.rs:446
   uint32_t z[N];          // GENERATOR^T = primitive_root_of_unity(TWO_ADICITY), Montgomery form (field.rs:445)
 };
@@ -83,13 +83,17 @@ template <class F>
 __device__ __noinline__ bool field_sqrt(const F& a, const CodecConsts<F::N>& k, F& root) {
   if (a.is_zero()) { root = a; return true; }
   const F one = F::one();
-  if (F::pow(a, k.qr_exp, F::Params::BITS) != one) return false;      // is_quadratic_residue
-  F z;
-#pragma unroll
-  for (int i = 0; i < F::N; ++i) z.l[i] = k.z[i];
+  // w, x, b exactly as field.rs:446-448.  Euler's criterion (is_quadratic_residue, field.rs:377-391) is evaluated on
+  // b = a^T instead of with a second full-length exponentiation: a^((p-1)/2) = (a^T)^(2^(s-1)), s = TWO_ADICITY.
   F w = F::pow(a, k.w_exp, F::Params::BITS);
   F x = F::mul(w, a);
   F b = F::mul(x, w);
+  F e = b;
+  for (int i = 0; i < F::Params::TWO_ADICITY - 1; ++i) e = F::sqr(e);
+  if (e != one) return false;
+  F z;
+#pragma unroll
+  for (int i = 0; i < F::N; ++i) z.l[i] = k.z[i];
   int v = F::Params::TWO_ADICITY;
   while (b != one) {
     int kk = 0;
