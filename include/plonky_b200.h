@@ -126,6 +126,12 @@ int plk_msm_execute_partial_dev(const plk_msm_table* t, const void* d_scalars, s
 int plk_msm_combine_partials_dev(int curve, const void* d_partials, size_t count, void* d_out_xyz,
                                  void* d_out_zero, void* stream);
 size_t plk_msm_partial_limbs(int curve);        /* u64 limbs of one partial (4*L) */
+/* msm_parallel (curve_msm.rs:54-61) on device buffers: d_points_xy n affine points (2*L u64 each, identity = (0, 0)),
+ * d_scalars n*4 u64.  Table-free variable-base path (per-window buckets + Horner); asynchronous on `stream`.  Shares no
+ * table, window choice or reduction kernel with plk_msm_execute_dev, which is why bench.py cross-checks one against the
+ * other. */
+int plk_msm_parallel_dev(int curve, const void* d_scalars, const void* d_points_xy, size_t n, void* d_out_xyz,
+                         void* d_out_zero, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * NTT  (src/fft.rs)

@@ -778,6 +778,108 @@ template <class C> static int gen_points_t(uint64_t seed, size_t n, uint64_t* ou
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// src/hash_to_curve.rs:13-76 -- blake_field / blake_hash_base_field_to_curve / blake_hash_usize_to_curve, the
+// derivation of pedersen_g (src/circuit_builder.rs:1127).  BLAKE3 is the blake3 crate (Cargo.toml: "0.3.3", not
+// vendored): restated from the published compression function for the one case the path needs (a single block
+// of at most 64 bytes in, at most 64 bytes of extended output), like oracle/plonky_oracle.py, and pinned by the
+// same golden vectors (tests/golden/blake_hash_to_curve.json, made with the independent `blake3` package).
+// ------------------------------------------------------------------------------------------
+static inline uint32_t rotr32(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+static void blake3_one_block(const uint8_t* data, size_t len, uint8_t out[64]) {
+  static const uint32_t IV[8] = {0x6A09E667u, 0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au, 0x510E527Fu, 0x9B05688Cu, 0x1F83D9ABu, 0x5BE0CD19u};
+  static const int PERM[16] = {2, 6, 3, 10, 7, 0, 4, 13, 1, 11, 12, 5, 9, 14, 15, 8};
+  uint8_t block[64] = {0};
+  memcpy(block, data, len);
+  uint32_t m[16], v[16];
+  for (int i = 0; i < 16; ++i) m[i] = (uint32_t)block[4 * i] | ((uint32_t)block[4 * i + 1] << 8) | ((uint32_t)block[4 * i + 2] << 16) | ((uint32_t)block[4 * i + 3] << 24);
+  for (int i = 0; i < 8; ++i) v[i] = IV[i];
+  for (int i = 0; i < 4; ++i) v[8 + i] = IV[i];
+  v[12] = 0; v[13] = 0; v[14] = (uint32_t)len; v[15] = 1 | 2 | 8;       // CHUNK_START | CHUNK_END | ROOT, counter 0
+  auto g = [&](int a, int b, int c, int d, uint32_t mx, uint32_t my) {
+    v[a] = v[a] + v[b] + mx; v[d] = rotr32(v[d] ^ v[a], 16);
+    v[c] = v[c] + v[d];      v[b] = rotr32(v[b] ^ v[c], 12);
+    v[a] = v[a] + v[b] + my; v[d] = rotr32(v[d] ^ v[a], 8);
+    v[c] = v[c] + v[d];      v[b] = rotr32(v[b] ^ v[c], 7);
+  };
+  for (int rnd = 0; rnd < 7; ++rnd) {
+    g(0, 4, 8, 12, m[0], m[1]); g(1, 5, 9, 13, m[2], m[3]); g(2, 6, 10, 14, m[4], m[5]); g(3, 7, 11, 15, m[6], m[7]);
+    g(0, 5, 10, 15, m[8], m[9]); g(1, 6, 11, 12, m[10], m[11]); g(2, 7, 8, 13, m[12], m[13]); g(3, 4, 9, 14, m[14], m[15]);
+    if (rnd < 6) { uint32_t t[16]; for (int i = 0; i < 16; ++i) t[i] = m[PERM[i]]; memcpy(m, t, sizeof(m)); }
+  }
+  for (int i = 0; i < 8; ++i) { v[i] ^= v[i + 8]; v[i + 8] ^= IV[i]; }
+  for (int i = 0; i < 16; ++i) for (int b = 0; b < 4; ++b) out[4 * i + b] = (uint8_t)(v[i] >> (8 * b));
+}
+// Field::square_root (field.rs:440-473) with is_quadratic_residue (:377-392, Euler's criterion): the reference's
+// Tonelli-Shanks loop, so the same one of the two roots comes out.
+template <class F> static bool fe_sqrt(const Fe<F>& a, Fe<F>* out) {
+  typedef Fe<F> E;
+  constexpr int N = F::N;
+  if (a.is_zero()) { *out = a; return true; }
+  const Big<N> pm1 = big_sub(E::order(), big_small<N>(1));
+  if (a.exp_big(big_div2(pm1)) != E::one()) return false;
+  const Big<N> t = E::from_limbs(F::T).to_canonical();
+  E z = E::from_limbs(F::GENERATOR).exp_big(t);
+  E w = a.exp_big(big_div2(big_sub(t, big_small<N>(1))));
+  E x = w * a, b = x * w;
+  int v = F::TWO_ADICITY;
+  while (b != E::one()) {
+    int k = 0;
+    E b2k = b;
+    while (b2k != E::one()) { b2k = b2k.square(); ++k; }
+    w = z;
+    for (int i = 0; i < v - k - 1; ++i) w = w.square();
+    z = w.square(); b = b * z; x = x * w; v = k;
+  }
+  *out = x;
+  return true;
+}
+template <class C> static Aff<C> blake_hash_base_field_to_curve(const Fe<typename C::Base>& seed) {
+  typedef typename C::Base F;
+  typedef Fe<F> E;
+  constexpr int N = F::N, NB = 8 * N;
+  const Big<N> sc = seed.to_canonical();
+  uint8_t msg[NB + 2];
+  for (int i = 0; i < NB; ++i) msg[i] = (uint8_t)(sc.l[i / 8] >> (8 * (i % 8)));
+  for (int it = 0; it < 256; ++it) {                         // hash_to_curve.rs:59-75
+    E x; bool y_neg = false;
+    for (int j = 0; j < 256; ++j) {                          // blake_field, :13-51
+      msg[NB] = (uint8_t)it; msg[NB + 1] = (uint8_t)j;
+      uint8_t h[64];
+      blake3_one_block(msg, NB + 2, h);
+      h[NB - 1] >>= (8 * NB - F::BITS);
+      Big<N> c;
+      for (int l = 0; l < N; ++l) { c.l[l] = 0; for (int b = 0; b < 8; ++b) c.l[l] |= (uint64_t)h[8 * l + b] << (8 * b); }
+      if (big_cmp(c, E::order()) < 0) { x = E::from_canonical(c); y_neg = h[NB] & 1; break; }
+    }
+    E cand = x.cube() + E::from_limbs(C::B);
+    if (!C::A_IS_ZERO) cand = cand + E::from_limbs(C::A) * x;
+    E y;
+    if (fe_sqrt<F>(cand, &y)) {
+      Aff<C> r; r.x = x; r.y = y_neg ? y.neg() : y; r.zero = false;
+      return r;
+    }
+  }
+  return aff_zero<C>();
+}
+template <class C> static int blake_points_t(uint64_t seed_start, size_t n, uint64_t* out_xy) {
+  typedef Fe<typename C::Base> E;
+#pragma omp parallel for schedule(dynamic, 64)
+  for (long i = 0; i < (long)n; ++i) {
+    uint8_t z;
+    store_affine(blake_hash_base_field_to_curve<C>(E::from_u64(seed_start + (uint64_t)i)), out_xy + 2 * i * C::Base::N, &z);
+  }
+  return 0;
+}
+extern "C" int ref_blake_hash_usize_to_curve(int cid, uint64_t seed_start, size_t n, uint64_t* out_xy) {
+  switch (cid) {
+    case 0: return blake_points_t<Tweedledee>(seed_start, n, out_xy);
+    case 1: return blake_points_t<Tweedledum>(seed_start, n, out_xy);
+    case 2: return blake_points_t<Bls12377>(seed_start, n, out_xy);
+  }
+  return -1;
+}
+
 extern "C" {
 void* ref_msm_precompute(int cid, const uint64_t* xy, const uint8_t* zero, size_t n, int w) {
   if (w < 1 || w > 24) return nullptr;

@@ -53,6 +53,7 @@ def lib(native: bool = False):
     L.ref_curve_mul.argtypes = [C.c_int, u64p, C.c_uint8, u64p, u64p, u8p]
     L.ref_affine_sum.argtypes = [C.c_int, u64p, u8p, C.c_size_t, C.c_int, u64p, u8p]
     L.ref_gen_points.argtypes = [C.c_int, C.c_uint64, C.c_size_t, u64p]
+    L.ref_blake_hash_usize_to_curve.argtypes = [C.c_int, C.c_uint64, C.c_size_t, u64p]
     L.ref_to_digits.argtypes = [C.c_int, u64p, C.c_int, u32p]
     L.ref_set_threads.argtypes = [C.c_int]
     L.ref_ipa_round_lr.argtypes = [C.c_int, u64p, u64p, u64p, u8p, C.c_size_t, u64p, u8p, u64p]
@@ -195,6 +196,14 @@ def gen_points(cid: int, seed: int, n: int, L=None):
     nl = FIELD_LIMBS[CURVE_BASE[cid]]
     out = np.empty((n, 2, nl), dtype=np.uint64)
     assert (L or lib()).ref_gen_points(cid, seed, n, _p64(out)) == 0
+    return out
+
+
+def blake_hash_usize_to_curve(cid: int, seed_start: int, n: int, L=None):
+    """[blake_hash_usize_to_curve(seed) for seed in seed_start .. seed_start + n) (hash_to_curve.rs:53-76): pedersen_g."""
+    nl = FIELD_LIMBS[CURVE_BASE[cid]]
+    out = np.zeros((n, 2, nl), dtype=np.uint64)
+    assert (L or lib()).ref_blake_hash_usize_to_curve(cid, seed_start, n, _p64(out)) == 0
     return out
 
 

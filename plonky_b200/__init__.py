@@ -108,6 +108,7 @@ def lib():
     L.plk_msm_execute_batch_dev.argtypes = [vp, vp, sz, sz, vp, vp, vp]
     L.plk_msm_execute_partial_dev.argtypes = [vp, vp, sz, vp, vp]
     L.plk_msm_combine_partials_dev.argtypes = [C.c_int, vp, sz, vp, vp, vp]
+    L.plk_msm_parallel_dev.argtypes = [C.c_int, vp, vp, sz, vp, vp, vp]
     L.plk_msm_partial_limbs.argtypes = [C.c_int]
     L.plk_msm_partial_limbs.restype = sz
     L.plk_fft_precompute.argtypes = [C.c_int, sz, C.POINTER(vp)]

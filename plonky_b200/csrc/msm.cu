@@ -345,6 +345,14 @@ int plk_msm_execute_batch_dev(const plk_msm_table* tc, const void* d_scalars, si
               reinterpret_cast<cudaStream_t>(stream));
   });
 }
+int plk_msm_parallel_dev(int curve, const void* d_scalars, const void* d_points_xy, size_t n, void* d_out_xyz, void* d_out_zero,
+                         void* stream) {
+  return guarded([&] {
+    if (curve_scalar_bits(curve) < 0) fail(PLK_EINVAL, "unknown curve id");
+    if ((n && (!d_scalars || !d_points_xy)) || !d_out_xyz || !d_out_zero) fail(PLK_EINVAL, "NULL buffer");
+    msm_variable_dev(curve, d_points_xy, d_scalars, n, d_out_xyz, d_out_zero, reinterpret_cast<cudaStream_t>(stream));
+  });
+}
 size_t plk_msm_partial_limbs(int curve) { return 4 * (size_t)curve_base_limbs64(curve); }
 
 int plk_points_generate_dev(int curve, uint64_t seed, size_t n, void* d_points_xy, void* stream) {

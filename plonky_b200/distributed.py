@@ -16,9 +16,10 @@ import torch
 import torch.distributed as dist
 
 from . import lib, _check, FIELD_LIMBS, CURVE_BASE_FIELD, MsmPrecomputation
+from .sharding import shard_range, partial_layout
 
 __all__ = ["msm_precompute_affine_dev", "points_generate_dev", "pedersen_generators_dev", "msm_execute_dev", "msm_execute_sharded", "msm_execute_batch_dev", "fft_dev",
-           "DistributedNtt"]
+           "msm_parallel_dev", "exchange_partials", "ShardedMsm", "DistributedNtt"]
 
 
 def _stream_ptr() -> C.c_void_p:
@@ -66,18 +67,75 @@ def msm_execute_batch_dev(pre: MsmPrecomputation, scalars_k: torch.Tensor, out_x
                                            C.c_void_p(out_zero.data_ptr()), _stream_ptr()))
 
 
+def msm_parallel_dev(curve: int, scalars: torch.Tensor, points_xy: torch.Tensor, out_xyz: torch.Tensor, out_zero: torch.Tensor):
+    """msm_parallel (curve_msm.rs:54-61) on device buffers, table-free: scalars (n, 4), points_xy (n, 2, L) int64."""
+    _check(lib().plk_msm_parallel_dev(curve, C.c_void_p(scalars.data_ptr()), C.c_void_p(points_xy.data_ptr()), scalars.shape[0],
+                                      C.c_void_p(out_xyz.data_ptr()), C.c_void_p(out_zero.data_ptr()), _stream_ptr()))
+
+
+def msm_execute_partial_dev(pre: MsmPrecomputation, scalars: torch.Tensor, partial: torch.Tensor):
+    """This shard's un-normalised sum (XYZZ, 4 L limbs) into `partial`."""
+    _check(lib().plk_msm_execute_partial_dev(pre.handle, C.c_void_p(scalars.data_ptr()), scalars.shape[0],
+                                             C.c_void_p(partial.data_ptr()), _stream_ptr()))
+
+
+def msm_combine_partials_dev(curve: int, gathered: torch.Tensor, count: int, out_xyz: torch.Tensor, out_zero: torch.Tensor):
+    """Sum of `count` gathered partials (layout: sharding.partial_layout) -> one normalised point."""
+    _check(lib().plk_msm_combine_partials_dev(curve, C.c_void_p(gathered.data_ptr()), count,
+                                              C.c_void_p(out_xyz.data_ptr()), C.c_void_p(out_zero.data_ptr()), _stream_ptr()))
+
+
+def exchange_partials(partial: torch.Tensor, gathered: torch.Tensor, group=None) -> torch.Tensor:
+    """The MSM's only collective: all-gather of the per-rank partials into the layout of sharding.partial_layout
+    (rank r's limbs at offset r * limbs).  Backend-agnostic (NCCL on device tensors, gloo in the CPU tests)."""
+    world = dist.get_world_size(group)
+    off, total = partial_layout(world, partial.numel())
+    assert gathered.numel() == total and off(world - 1) + partial.numel() == total
+    dist.all_gather_into_tensor(gathered, partial, group=group)
+    return gathered
+
+
 def msm_execute_sharded(pre: MsmPrecomputation, scalars: torch.Tensor, partial: torch.Tensor, gathered: torch.Tensor,
                         out_xyz: torch.Tensor, out_zero: torch.Tensor, group=None):
     """This rank's shard -> partial; all-gather; combine.  With world_size 1 it is msm_execute_dev."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return msm_execute_dev(pre, scalars, out_xyz, out_zero)
-    L = lib()
-    _check(L.plk_msm_execute_partial_dev(pre.handle, C.c_void_p(scalars.data_ptr()), scalars.shape[0],
-                                         C.c_void_p(partial.data_ptr()), _stream_ptr()))
-    dist.all_gather_into_tensor(gathered, partial, group=group)
-    _check(L.plk_msm_combine_partials_dev(pre.curve, C.c_void_p(gathered.data_ptr()), world,
-                                          C.c_void_p(out_xyz.data_ptr()), C.c_void_p(out_zero.data_ptr()), _stream_ptr()))
+    msm_execute_partial_dev(pre, scalars, partial)
+    exchange_partials(partial, gathered, group)
+    msm_combine_partials_dev(pre.curve, gathered, world, out_xyz, out_zero)
+
+
+class ShardedMsm:
+    """An n-term fixed-base MSM split over the ranks of `group`: rank r owns the terms
+    sharding.shard_range(n, world, r), builds the table of its generators only and keeps the exchange buffers.
+
+      sm = ShardedMsm(curve, n_total, make_points=lambda lo, hi: <(hi - lo, 2, L) device tensor>)
+      sm.execute(local_scalars) -> (out_xyz, out_zero) device tensors, identical on every rank
+    """
+
+    def __init__(self, curve: int, n_total: int, make_points, w: int = 11, group=None, world: int = None, rank: int = None):
+        self.curve, self.group = curve, group
+        self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
+        self.rank = rank if rank is not None else (dist.get_rank(group) if dist.is_initialized() else 0)
+        self.lo, self.hi = shard_range(n_total, self.world, self.rank)
+        Lb = FIELD_LIMBS[CURVE_BASE_FIELD[curve]]
+        self.points = make_points(self.lo, self.hi)
+        self.table = msm_precompute_affine_dev(curve, self.points, w)
+        limbs = 4 * Lb
+        _, total = partial_layout(self.world, limbs)
+        self.partial = torch.zeros(limbs, dtype=torch.int64, device="cuda")
+        self.gathered = torch.zeros(total, dtype=torch.int64, device="cuda")
+        self.out_xyz = torch.zeros((3, Lb), dtype=torch.int64, device="cuda")
+        self.out_zero = torch.zeros(8, dtype=torch.uint8, device="cuda")
+
+    def __len__(self):
+        return self.hi - self.lo
+
+    def execute(self, local_scalars: torch.Tensor):
+        assert local_scalars.shape[0] == self.hi - self.lo
+        msm_execute_sharded(self.table, local_scalars, self.partial, self.gathered, self.out_xyz, self.out_zero, self.group)
+        return self.out_xyz, self.out_zero
 
 
 def fft_dev(pre, d_in: torch.Tensor, d_out: torch.Tensor, inverse: bool = False, coset: bool = False):

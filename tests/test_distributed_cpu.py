@@ -1,5 +1,7 @@
-"""Multi-GPU host logic on CPU (gloo, world_size 2): shard boundaries and the all-gather layout that
-plk_msm_combine_partials_dev consumes.  The CUDA side of the N > 1 path is exercised by bench.py --gpus N."""
+"""Multi-GPU host logic on CPU (gloo, world_size 2): the shard boundaries plonky_b200.distributed.ShardedMsm uses and
+the product's own collective step (distributed.exchange_partials, the all-gather whose layout
+plk_msm_combine_partials_dev consumes) run here on CPU tensors.  The CUDA side of the sharded path (partial + combine
+kernels) is parity-tested on one GPU in tests/test_gpu_sharded.py."""
 import os
 import socket
 
@@ -10,6 +12,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from plonky_b200.sharding import shard_range, partial_layout
+from plonky_b200 import distributed as pkd
 
 
 def test_shard_range_partitions_everything():
@@ -31,7 +34,7 @@ def _worker(rank, world, port, q):
     off, total = partial_layout(world, limbs)
     partial = torch.full((limbs,), rank + 1, dtype=torch.int64)
     gathered = torch.zeros(total, dtype=torch.int64)
-    dist.all_gather_into_tensor(gathered, partial)
+    pkd.exchange_partials(partial, gathered)            # the product's collective step, gloo instead of NCCL
     ok = all(bool((gathered[off(r):off(r) + limbs] == r + 1).all()) for r in range(world))
     # a scalar vector is split exactly like the generator table
     n = 1001

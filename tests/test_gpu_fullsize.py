@@ -114,3 +114,36 @@ def test_coset_lde_full_size():
     cr = rand_limbs(n_in, 21)
     back = pk.coset_ifft(pk.coset_lde(cr, pre), pre)
     assert np.array_equal(back[:n_in], cr) and not back[n_in:].any()
+
+
+# ---- dense comparisons at BASELINE's full sizes against the C++ restatement of the reference ----------------------
+def test_ntt_full_size_dense_vs_port():
+    """NTT 2^24 forward and inverse, every output word against fft_with_precomputation_power_of_2 /
+    ifft_with_precomputation_power_of_2 (fft.rs:82-156) restated in oracle/ref_port.cpp."""
+    import ref_port as rp
+    f = po.TWEEDLEDEE_BASE
+    n = 1 << 24
+    x = rand_limbs(n, 2024)
+    pre = pk.fft_precompute(f.fid, n)
+    port = rp.FftPlan(f.fid, n)
+    got = pk.fft_with_precomputation_power_of_2(x, pre)
+    assert np.array_equal(got, port.run(x))
+    got_inv = pk.ifft_with_precomputation_power_of_2(x, pre)
+    assert np.array_equal(got_inv, port.run(x, inverse=True))
+
+
+@pytest.mark.parametrize("name,logn", [("Tweedledee", 20), ("Bls12377", 19)])
+def test_msm_full_size_pedersen_g_vs_port(name, logn):
+    """bench.py's actual input -- pedersen_g = blake_hash_usize_to_curve(i) (circuit_builder.rs:1127), 2^20 terms
+    (BLS12-377: 2^19, the per-GPU shard of BASELINE config 4) -- against msm_execute_parallel with w = 11
+    (curve_msm.rs:102-157) restated in oracle/ref_port.cpp."""
+    import ref_port as rp
+    c = po.CURVES[name]
+    n = 1 << logn
+    g = pk.blake_hash_usize_to_curve(c.cid, 0, n)
+    S = rand_limbs(n, 77)
+    if name == "Bls12377":
+        S[:, 3] >>= np.uint64(2)
+    out, oz = pk.msm_execute_parallel(pk.msm_precompute_affine(c.cid, g, 11), S)
+    want_xy, want_zero = rp.MsmTable(c.cid, g, None, 11).execute(S, parallel=True)
+    assert oz == want_zero and np.array_equal(out[:2], want_xy)
