@@ -95,6 +95,11 @@ int plk_msm_precompute_affine(int curve, const uint64_t* points_xy, const uint8_
 size_t plk_msm_table_len(const plk_msm_table* t);
 unsigned plk_msm_table_window(const plk_msm_table* t);   /* the w the caller passed */
 void plk_msm_free(plk_msm_table* t);
+/* Geometry the device chose for this table (measurement / bench.py): out[0] = window bits c, out[1] = number of
+ * windows, out[2] = bucket accumulation mode (0: XYZZ mixed additions, 1: batched-affine tree), out[3] = Montgomery
+ * products per mixed XYZZ addition (10; a batched-affine addition is 6), out[4] = batched-affine rounds in front of the
+ * XYZZ stage.  Returns the number of values written (<= cap). */
+int plk_msm_table_info(const plk_msm_table* t, unsigned* out, int cap);
 
 /* msm_execute / msm_execute_parallel(&precomputation, scalars) (curve_msm.rs:63, :102) and
  * pedersen_hash (src/plonk_util.rs:193-198).  n must equal the table length (PLK_ELENGTH). */
@@ -105,6 +110,13 @@ int plk_msm_execute(const plk_msm_table* t, const uint64_t* scalars, size_t n,
  * out_xyz k*3*L limbs, out_zero k bytes. */
 int plk_msm_execute_batch(const plk_msm_table* t, const uint64_t* scalars, size_t n, size_t k,
                           uint64_t* out_xyz, uint8_t* out_zero);
+/* commit_polynomials -> PolynomialCommitment::coeffs_vec_to_commitments (src/plonk_util.rs:215-231,
+ * src/poly_commit.rs:32-66) in ONE call: for each of the k coefficient vectors (k*n*4 limbs) the commitment
+ * pedersen_hash(coeffs_i) + [blinding_i] * H, then batch_to_affine over all k.  blinding: k*4 limbs (the factors the
+ * caller drew, poly_commit.rs:39-43: the RNG stays with the caller) or NULL for blinding = false; h_xy / h_zero: the
+ * blinding point (pedersen_h).  out_xy: k affine points (2*L limbs each), out_zero: k flags. */
+int plk_commit_batch(const plk_msm_table* t, const uint64_t* scalars, size_t n, size_t k, const uint64_t* blinding,
+                     const uint64_t* h_xy, uint8_t h_zero, uint64_t* out_xy, uint8_t* out_zero);
 /* msm_parallel(scalars, generators, w) = precompute + execute (curve_msm.rs:54-61), used with
  * changing bases by the Halo IPA (src/halo.rs:87,91,122): no table is kept. */
 int plk_msm_parallel(int curve, const uint64_t* scalars, const uint64_t* points_xyz,
@@ -217,6 +229,11 @@ int plk_fft_dist_phase_b(const plk_fft_plan* plan_n, void* d_recv, unsigned log_
  * 0 add, 1 sub, 2 mul, 3 square, 4 neg, 5 inverse (Fermat ladder), 6 to_canonical, 7 from_canonical, 8 double,
  * 9 inverse by the binary extended GCD (the reference's algorithm, src/bigint/bigint_inverse.rs:6-55) */
 int plk_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
+/* Field ToBytes / FromBytes (src/serialization.rs:17-30): n elements <-> n * 8*L bytes, the canonical value
+ * little-endian (to_canonical_u8_vec).  from_bytes returns PLK_EINVAL ("Out of range") for a value >= the modulus,
+ * where the reference returns io::Error. */
+int plk_field_to_bytes(int field, const uint64_t* in, size_t n, uint8_t* out);
+int plk_field_from_bytes(int field, const uint8_t* in, size_t n, uint64_t* out);
 /* Field::batch_multiplicative_inverse (src/field/field.rs:251-278); PLK_EZERO if any input is 0 */
 int plk_batch_inverse(int field, const uint64_t* in, uint64_t* out, size_t n);
 /* ProjectivePoint::batch_to_affine (src/curve/curve.rs:216-232) */

@@ -30,10 +30,10 @@ __all__ = [
     "TWEEDLEDEE_BASE", "TWEEDLEDUM_BASE", "BLS12_377_SCALAR", "BLS12_377_BASE",
     "TWEEDLEDEE", "TWEEDLEDUM", "BLS12_377",
     "MsmPrecomputation", "msm_precompute", "msm_precompute_affine", "msm_execute", "msm_execute_parallel",
-    "msm_execute_batch", "msm_parallel", "pedersen_hash",
+    "msm_execute_batch", "msm_parallel", "pedersen_hash", "coeffs_vec_to_commitments", "commit_polynomials", "msm_table_info",
     "FftPrecomputation", "fft_precompute", "fft", "fft_with_precomputation", "fft_with_precomputation_power_of_2",
     "ifft_with_precomputation_power_of_2", "fft_batch", "coset_lde", "coset_ifft", "divide_by_z_h",
-    "field_op", "batch_multiplicative_inverse", "batch_to_affine", "affine_summation_best", "affine_multisummation_best", "curve_mul", "points_generate", "kernel_launch_count",
+    "field_op", "field_to_bytes", "field_from_bytes", "batch_multiplicative_inverse", "batch_to_affine", "affine_summation_best", "affine_multisummation_best", "curve_mul", "points_generate", "kernel_launch_count",
     "polynomial_mul", "eval_domain", "from_evaluations", "permutation_polynomial",
     "HaloIpaRounds", "blake_hash_usize_to_curve", "blake_hash_base_field_to_curve", "points_to_bytes", "points_from_bytes",
 ]
@@ -99,6 +99,7 @@ def lib():
     L.plk_msm_table_len.restype = sz
     L.plk_msm_table_window.argtypes = [vp]
     L.plk_msm_table_window.restype = C.c_uint
+    L.plk_msm_table_info.argtypes = [vp, C.POINTER(C.c_uint), C.c_int]
     L.plk_msm_free.argtypes = [vp]
     L.plk_msm_free.restype = None
     L.plk_msm_execute.argtypes = [vp, u64p, sz, u64p, u8p]
@@ -108,6 +109,7 @@ def lib():
     L.plk_msm_execute_batch_dev.argtypes = [vp, vp, sz, sz, vp, vp, vp]
     L.plk_msm_execute_partial_dev.argtypes = [vp, vp, sz, vp, vp]
     L.plk_msm_combine_partials_dev.argtypes = [C.c_int, vp, sz, vp, vp, vp]
+    L.plk_commit_batch.argtypes = [vp, u64p, sz, sz, u64p, u64p, C.c_uint8, u64p, u8p]
     L.plk_msm_parallel_dev.argtypes = [C.c_int, vp, vp, sz, vp, vp, vp]
     L.plk_msm_partial_limbs.argtypes = [C.c_int]
     L.plk_msm_partial_limbs.restype = sz
@@ -130,6 +132,8 @@ def lib():
     L.plk_fft_dist_phase_b.argtypes = [vp, vp, C.c_uint, C.c_uint, C.c_uint, vp]
     L.plk_field_op.argtypes = [C.c_int, C.c_int, u64p, u64p, u64p, sz]
     L.plk_batch_inverse.argtypes = [C.c_int, u64p, u64p, sz]
+    L.plk_field_to_bytes.argtypes = [C.c_int, u64p, sz, u8p]
+    L.plk_field_from_bytes.argtypes = [C.c_int, u8p, sz, u64p]
     L.plk_batch_to_affine.argtypes = [C.c_int, u64p, u8p, sz, u64p, u8p]
     L.plk_affine_summation.argtypes = [C.c_int, u64p, u8p, sz, u64p, u8p]
     L.plk_affine_multisummation.argtypes = [C.c_int, u64p, u8p, u64p, sz, u64p, u8p]
@@ -211,6 +215,15 @@ def measure_mul_throughput(field: int) -> float:
     v = C.c_double()
     _check(lib().plk_measure_mul_throughput(field, C.byref(v)))
     return float(v.value)
+
+
+def msm_table_info(pre: "MsmPrecomputation") -> dict:
+    """The geometry the device chose for a table: window bits, windows, accumulation mode, products per bucket addition."""
+    buf = (C.c_uint * 5)()
+    k = lib().plk_msm_table_info(pre.handle, buf, 5)
+    assert k == 5
+    return {"c": int(buf[0]), "nwin": int(buf[1]), "mode": ("xyzz", "batched-affine + xyzz")[int(buf[2])], "products_per_add": int(buf[3]),
+            "affine_rounds": int(buf[4])}
 
 
 def msm_last_phase_ms(pre: "MsmPrecomputation"):
@@ -304,6 +317,30 @@ def msm_execute_batch(precomputation: MsmPrecomputation, scalars_k):
     oz = np.zeros(k, dtype=np.uint8)
     _check(lib().plk_msm_execute_batch(precomputation.handle, _p64(s), n, k, _p64(out), _p8(oz)))
     return out, oz.astype(bool)
+
+
+def coeffs_vec_to_commitments(coefficients_vec, msm_precomputation: MsmPrecomputation, blinding_point_xy, blinding_factors=None,
+                              blinding_point_zero: bool = False):
+    """PolynomialCommitment::coeffs_vec_to_commitments / commit_polynomials (src/poly_commit.rs:52-66,
+    src/plonk_util.rs:215-231) in one device call: ((k, 2, L) affine commitments, (k,) zero flags).  blinding_factors:
+    (k, 4) scalars for `blinding = true` (the caller draws them, poly_commit.rs:39-43) or None for `blinding = false`."""
+    curve = msm_precomputation.curve
+    Lb = FIELD_LIMBS[CURVE_BASE_FIELD[curve]]
+    s = _u64(coefficients_vec)
+    k, n = s.shape[0], s.shape[1]
+    s = s.reshape(k, n, 4)
+    h = _u64(blinding_point_xy).reshape(2, Lb)
+    bl = None
+    if blinding_factors is not None:
+        bl = _u64(blinding_factors).reshape(k, 4)
+    out = np.zeros((k, 2, Lb), dtype=np.uint64)
+    oz = np.zeros(k, dtype=np.uint8)
+    _check(lib().plk_commit_batch(msm_precomputation.handle, _p64(s), n, k, _p64(bl) if bl is not None else None, _p64(h),
+                                  1 if blinding_point_zero else 0, _p64(out), _p8(oz)))
+    return out, oz.astype(bool)
+
+
+commit_polynomials = coeffs_vec_to_commitments
 
 
 def msm_parallel(curve: int, scalars, generators, w: int, zero=None):
@@ -444,6 +481,24 @@ def field_op(field: int, op: str, a, b=None) -> np.ndarray:
     out = np.empty_like(a)
     bp = _p64(_u64(b).reshape(-1, L)) if b is not None else None
     _check(lib().plk_field_op(field, _OPS[op], _p64(a), bp, _p64(out), a.shape[0]))
+    return out
+
+
+def field_to_bytes(field: int, x) -> np.ndarray:
+    """Field ToBytes (src/serialization.rs:17-21): (n, 8 L) bytes, to_canonical_u8_vec per element."""
+    L = FIELD_LIMBS[field]
+    a = _u64(x).reshape(-1, L)
+    out = np.zeros((a.shape[0], 8 * L), dtype=np.uint8)
+    _check(lib().plk_field_to_bytes(field, _p64(a), a.shape[0], _p8(out)))
+    return out
+
+
+def field_from_bytes(field: int, data) -> np.ndarray:
+    """Field FromBytes (src/serialization.rs:23-30): ValueError("Out of range") where the reference returns io::Error."""
+    L = FIELD_LIMBS[field]
+    d = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1, 8 * L)
+    out = np.zeros((d.shape[0], L), dtype=np.uint64)
+    _check(lib().plk_field_from_bytes(field, _p8(d), d.shape[0], _p64(out)))
     return out
 
 

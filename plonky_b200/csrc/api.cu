@@ -1,6 +1,8 @@
 // Process-wide plumbing of the C ABI (status strings, error capture, per-thread streams and scratch)
 // and the small elementwise entry points: plk_field_op, plk_batch_inverse.
 #include <mutex>
+#include <string.h>
+#include <vector>
 #include "common.cuh"
 #include "fp.cuh"
 
@@ -301,6 +303,12 @@ void launch_permutation(const PermArgs& a, void* d_num, void* d_den, void* d_inv
 
 using namespace plk;
 
+template <class P>
+static void field_modulus64(const uint64_t** out) {
+  static uint64_t m[P::LIMBS / 2];
+  for (int i = 0; i < P::LIMBS / 2; ++i) m[i] = (uint64_t)P::mod(2 * i) | ((uint64_t)P::mod(2 * i + 1) << 32);
+  *out = m;
+}
 #define PLK_FIELD_DISPATCH(field, FN, ...)                                         \
   switch (field) {                                                                 \
     case PLK_FIELD_TWEEDLEDEE_BASE: FN<TweedledeeBaseParams>(__VA_ARGS__); break;  \
@@ -397,6 +405,37 @@ int plk_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64
     PLK_FIELD_DISPATCH(field, launch_field_op, op, da, b ? db : nullptr, dout, n, st);
     PLK_CUDA(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, st));
     PLK_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+// Field ToBytes / FromBytes (src/serialization.rs:17-30): to_canonical_u8_vec = the canonical value as 8*L little-endian
+// bytes; from_canonical_u8_vec fails with "Out of range" for values >= the modulus (src/field/field.rs, the
+// `from_canonical_u64_vec` check of every field).  The Montgomery <-> canonical conversions run on the device.
+int plk_field_to_bytes(int field, const uint64_t* in, size_t n, uint8_t* out) {
+  // little-endian host: the canonical limbs ARE the bytes
+  return plk_field_op(field, 6, in, nullptr, reinterpret_cast<uint64_t*>(out), n);
+}
+int plk_field_from_bytes(int field, const uint8_t* in, size_t n, uint64_t* out) {
+  return guarded([&] {
+    const int L = plk_field_limbs(field);
+    if (!L) fail(PLK_EINVAL, "unknown field id");
+    if (n == 0) return;
+    if (!in || !out) fail(PLK_EINVAL, "NULL buffer");
+    // p - 1 in canonical form = to_canonical(NEG_ONE); the modulus limbs are host constants of the tables
+    const uint64_t* mod = nullptr;
+    PLK_FIELD_DISPATCH(field, field_modulus64, &mod);
+    std::vector<uint64_t> tmp((size_t)n * L);
+    memcpy(tmp.data(), in, (size_t)n * L * 8);
+    for (size_t i = 0; i < n; ++i) {
+      bool less = false;
+      for (int j = 0; j < L; ++j) {                       // most significant limb decides last
+        const uint64_t a = tmp[i * L + j], m = mod[j];
+        less = a < m || (a == m && less);
+      }
+      if (!less) fail(PLK_EINVAL, "Out of range");
+    }
+    const int rc = plk_field_op(field, 7, tmp.data(), nullptr, out, n);
+    if (rc != PLK_OK) fail(rc, plk_last_error_message());
   });
 }
 

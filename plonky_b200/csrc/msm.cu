@@ -69,9 +69,10 @@ plk_msm_scratch* scratch_for(plk_msm_table* t, cudaStream_t st) {
   if (it == t->scratch.end()) {
     const MsmGeom& g = t->g;
     const size_t entries = (size_t)g.n * g.nwin;
-    t->max_tasks = entries / g.task + g.nb + 1;
+    t->max_tasks = ((entries >> g.affine_rounds) + g.nb) / g.task + g.nb + 1;
     const size_t xyzz = 2 * t->point_bytes;
     auto* s = new plk_msm_scratch();
+    s->affine_rounds = g.affine_rounds;
     if (t->temporary)
       for (plk::DevBuf* b : {&s->counts, &s->offsets, &s->task_off, &s->cursors, &s->sorted, &s->partials, &s->buckets, &s->ranges, &s->big_list,
                              &s->cta_hist})
@@ -86,6 +87,14 @@ plk_msm_scratch* scratch_for(plk_msm_table* t, cudaStream_t st) {
       s->buckets.alloc((size_t)g.nb * xyzz);
       s->ranges.alloc(((size_t)g.nb / kRangeSize + 1) * xyzz);
       s->big_list.alloc(((size_t)g.nb + 1) * 4);
+      if (g.affine_rounds > 0) {
+        // round r leaves at most entries / 2^r + nb points (every bucket rounds up)
+        const size_t t1 = (entries >> 1) + g.nb + 1, t2 = (entries >> 2) + g.nb + 1;
+        s->aff[0].alloc(t1 * t->point_bytes);
+        if (g.affine_rounds > 1) s->aff[1].alloc(t2 * t->point_bytes);
+        s->aff_prefix.alloc(t1 * (t->point_bytes / 2));
+        for (int r = 0; r < g.affine_rounds; ++r) s->aff_off[r].alloc(((size_t)g.nb + 1) * 4);
+      }
       // fixed-base geometry whose histogram fits in shared memory: per-CTA histograms instead of global atomics
       static const bool smem_sort = !(getenv("PLK_MSM_SORT") && atoi(getenv("PLK_MSM_SORT")) == 0);
       if (smem_sort && !g.variable && g.nb <= kSortMaxBins && g.n >= 4096) {
@@ -109,7 +118,7 @@ plk_msm_scratch* scratch_for(plk_msm_table* t, cudaStream_t st) {
 }
 void alloc_scratch(plk_msm_table* t) {
   const MsmGeom& g = t->g;
-  t->max_tasks = (size_t)g.n * g.nwin / g.task + g.nb + 1;
+  t->max_tasks = ((((size_t)g.n * g.nwin) >> g.affine_rounds) + g.nb) / g.task + g.nb + 1;
 }
 void run_one(plk_msm_table* t, const void* d_scalars, void* d_out_xyz, void* d_out_zero, void* d_partial, cudaStream_t st) {
   ops_for(t->curve)->execute_one(t, scratch_for(t, st), d_scalars, d_out_xyz, d_out_zero, d_partial, st);
@@ -159,12 +168,24 @@ plk_msm_table* new_table(int curve, size_t n, unsigned w, bool variable = false)
   t->g.nwin = (bits + 1 + t->g.c - 1) / t->g.c;
   t->g.nbw = 1u << (t->g.c - 1);
   t->g.nb = variable ? t->g.nbw * (unsigned)t->g.nwin : t->g.nbw;
+  // Batched-affine tree rounds in front of the XYZZ task kernel (msm_affine.cuh).  OFF by default: measured on B200 at
+  // 2^20 terms (profiles/r2_msm_affine_round_ncu.txt) the first round is bound by the random 64-byte gathers of the table
+  // walk, which it has to do twice (denominators, then the additions): 4.7 GB of DRAM reads at the ~2.6 TB/s random-access
+  // ceiling (tools/gather_probe.cu) = 1.54 ms for 8.4 M additions, against 1.26 ms for the same additions as mixed XYZZ
+  // additions that read every point once.  PLK_MSM_AFFINE_ROUNDS=1..3 enables it (parity-tested for all three).
   // task size: aim at >= ~75 K accumulate threads (4 CTAs of 128 on each of the 148 SMs) so that small MSMs
-  // still fill the machine; large ones use the full 64-entry tasks
+  // still fill the machine; large ones use the full 32-entry tasks
   {
     const unsigned long long entries = (unsigned long long)n * t->g.nwin;
+    int rounds = 0;
+    if (const char* e = getenv("PLK_MSM_AFFINE_ROUNDS")) { int v = atoi(e); if (v >= 0 && v <= kAffineRoundsHostMax && !variable) rounds = v; }
+    t->g.affine_rounds = rounds;
+    const unsigned long long left = entries >> rounds;          // entries the XYZZ stage still sees
     unsigned s = kTaskSizeMax;
-    while (s > 8 && entries / s < 75000) s >>= 1;
+    while (s > 8 && left / s < 75000) s >>= 1;
+    // very long buckets (2^21+ terms on one GPU): keep the task partials per bucket near 16, otherwise every bucket
+    // overflows into the one-CTA-per-bucket reduction (measured: BLS12-377 2^22 on one GPU, bucket_sum 50 ms)
+    while ((left / (t->g.nb ? t->g.nb : 1)) / s > 16 && s < 1024) s <<= 1;
     if (const char* e = getenv("PLK_MSM_TASK")) { int v = atoi(e); if (v >= 1 && v <= 1024) s = (unsigned)v; }
     t->g.task = s;
   }
@@ -274,6 +295,13 @@ int plk_msm_precompute_affine_dev(int curve, const void* d_points_xy, size_t n, 
 size_t plk_msm_table_len(const plk_msm_table* t) { return t ? t->n : 0; }
 unsigned plk_msm_table_window(const plk_msm_table* t) { return t ? t->w : 0; }
 void plk_msm_free(plk_msm_table* t) { delete t; }
+int plk_msm_table_info(const plk_msm_table* t, unsigned* out, int cap) {
+  if (!t || !out) return 0;
+  const unsigned v[5] = {(unsigned)t->g.c, (unsigned)t->g.nwin, t->g.affine_rounds > 0 ? 1u : 0u, 10u, (unsigned)t->g.affine_rounds};
+  int k = 0;
+  for (; k < cap && k < 5; ++k) out[k] = v[k];
+  return k;
+}
 
 int plk_msm_execute(const plk_msm_table* t, const uint64_t* scalars, size_t n, uint64_t* out_xyz, uint8_t* out_zero) {
   return guarded([&] { execute_host(const_cast<plk_msm_table*>(t), scalars, n, 1, out_xyz, out_zero); });
@@ -343,6 +371,30 @@ int plk_msm_execute_batch_dev(const plk_msm_table* tc, const void* d_scalars, si
     if ((n && !d_scalars) || !d_out_xyz || !d_out_zero) fail(PLK_EINVAL, "NULL buffer");
     run_batch(t, reinterpret_cast<const char*>(d_scalars), k, reinterpret_cast<char*>(d_out_xyz), reinterpret_cast<char*>(d_out_zero),
               reinterpret_cast<cudaStream_t>(stream));
+  });
+}
+int plk_commit_batch(const plk_msm_table* tc, const uint64_t* scalars, size_t n, size_t k, const uint64_t* blinding, const uint64_t* h_xy,
+                     uint8_t h_zero, uint64_t* out_xy, uint8_t* out_zero) {
+  return guarded([&] {
+    auto* t = const_cast<plk_msm_table*>(tc);
+    if (!t) fail(PLK_EINVAL, "NULL table");
+    if (n != t->n) fail(PLK_ELENGTH, "precomputation / scalars length mismatch");   // curve_msm.rs:106
+    if (k == 0) return;
+    if ((n && !scalars) || !out_xy || !out_zero || (blinding && !h_xy && !h_zero)) fail(PLK_EINVAL, "NULL buffer");
+    cudaStream_t st = thread_stream();
+    const size_t L = curve_base_limbs64(t->curve), sbytes = n * 32;
+    char* d_s = reinterpret_cast<char*>(thread_scratch(0, sbytes * k + 16));
+    // msm results (k * 3L u64 + k flags), blinding factors, outputs (k * 2L u64 + k flags)
+    const size_t o_msm = 0, o_mz = k * 3 * L * 8, o_bl = o_mz + ((k + 15) / 16) * 16, o_out = o_bl + k * 32, o_oz = o_out + k * 2 * L * 8;
+    char* d_o = reinterpret_cast<char*>(thread_scratch(1, o_oz + k + 16));
+    if (n) PLK_CUDA(cudaMemcpyAsync(d_s, scalars, sbytes * k, cudaMemcpyHostToDevice, st));
+    if (blinding) PLK_CUDA(cudaMemcpyAsync(d_o + o_bl, blinding, k * 32, cudaMemcpyHostToDevice, st));
+    run_batch(t, d_s, k, d_o + o_msm, d_o + o_mz, st);
+    ops_for(t->curve)->commit_blind(d_o + o_msm, reinterpret_cast<unsigned char*>(d_o + o_mz), blinding ? d_o + o_bl : nullptr, h_xy, h_zero != 0, k,
+                                    d_o + o_out, reinterpret_cast<unsigned char*>(d_o + o_oz), st);
+    PLK_CUDA(cudaMemcpyAsync(out_xy, d_o + o_out, k * 2 * L * 8, cudaMemcpyDeviceToHost, st));
+    PLK_CUDA(cudaMemcpyAsync(out_zero, d_o + o_oz, k, cudaMemcpyDeviceToHost, st));
+    PLK_CUDA(cudaStreamSynchronize(st));
   });
 }
 int plk_msm_parallel_dev(int curve, const void* d_scalars, const void* d_points_xy, size_t n, void* d_out_xyz, void* d_out_zero,

@@ -235,6 +235,10 @@ __device__ __forceinline__ XYZZ<C> load_xyzz(const void* base, size_t idx) {
   return p;
 }
 
+}  // namespace plk
+#include "msm_affine.cuh"
+namespace plk {
+
 // one thread per task: task t of bucket b adds entries [offsets[b] + k S, min(offsets[b+1], .. + S))
 template <class C>
 __global__ void __launch_bounds__(kAccThreads) msm_accumulate_kernel(const void* __restrict__ table, const unsigned* __restrict__ sorted,
@@ -610,6 +614,38 @@ __global__ void __launch_bounds__(64) curve_mul_kernel(const void* __restrict__ 
   out_zero[i] = z ? 1 : 0;
 }
 
+// ---- blinded commitments, src/poly_commit.rs:32-66 -----------------------------------------------------
+// coeffs_to_commitment: pedersen_hash(coeffs) + [blinding_factor] * blinding_point, then batch_to_affine over the k
+// commitments.  One thread per commitment: the MSM results arrive normalised (msm_xyz: x, y, z per commitment), the
+// blinding term is a plain double-and-add (one point, k scalars), one inversion each for the final affine form.
+template <class C>
+__global__ void __launch_bounds__(64) commit_blind_kernel(const uint32_t* __restrict__ msm_xyz, const unsigned char* __restrict__ msm_zero,
+                                                          const void* __restrict__ blinding, Affine<C> h, unsigned long long k,
+                                                          void* __restrict__ out_xy, unsigned char* __restrict__ out_zero) {
+  typedef Fp<typename C::Base> F;
+  typedef Fp<typename C::Scalar> SF;
+  const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (i >= k) return;
+  Affine<C> m = Affine<C>::identity();
+  if (!msm_zero[i]) {
+    const uint32_t* p = msm_xyz + (size_t)i * 3 * F::N;
+    for (int j = 0; j < F::N; ++j) { m.x.l[j] = p[j]; m.y.l[j] = p[F::N + j]; }
+  }
+  XYZZ<C> acc = XYZZ<C>::identity();
+  if (blinding) {
+    const SF s = SF::to_canonical(load_fp<SF>(blinding, i));
+    for (int bit = SF::N * 32 - 1; bit >= 0; --bit) {
+      acc = XYZZ<C>::dbl(acc);
+      if ((s.l[bit >> 5] >> (bit & 31)) & 1) acc = XYZZ<C>::madd(acc, h);
+    }
+  }
+  acc = XYZZ<C>::madd(acc, m);
+  const Affine<C> a = XYZZ<C>::to_affine(acc);
+  store_fp<F>(out_xy, 2 * i, a.x);
+  store_fp<F>(out_xy, 2 * i + 1, a.y);
+  out_zero[i] = acc.is_identity() ? 1 : 0;
+}
+
 // ---- host-side launch templates ----
 
 template <class C>
@@ -636,6 +672,24 @@ void import_points(const void* d_raw, const unsigned char* d_zero, size_t n, int
   if (n == 0) return;
   unsigned blocks = (unsigned)((n + 127) / 128);
   msm_import_points_kernel<C><<<blocks, 128, 0, st>>>(d_raw, d_zero, n, projective, d_out);
+  PLK_LAUNCHED();
+}
+
+// bucket offsets + task offsets (+ the per-round offsets of the batched-affine tree)
+static inline void launch_scan(plk_msm_scratch* s, const MsmGeom& g, cudaStream_t st) {
+  if (g.affine_rounds == 0) {
+    msm_scan_kernel<<<1, 1024, 0, st>>>(s->counts.as<unsigned>(), g.nb, g.task, s->offsets.as<unsigned>(), s->task_off.as<unsigned>(),
+                                        s->cursors.as<unsigned>());
+  } else {
+    AffineRoundOffsets ro;
+    for (int r = 0; r < kAffineRoundsMax; ++r) ro.off[r] = r < g.affine_rounds ? s->aff_off[r].as<unsigned>() : nullptr;
+    if (g.affine_rounds == 1)
+      msm_scan_rounds_kernel<1><<<1, 1024, 0, st>>>(s->counts.as<unsigned>(), g.nb, g.task, s->offsets.as<unsigned>(), ro, s->task_off.as<unsigned>(), s->cursors.as<unsigned>());
+    else if (g.affine_rounds == 2)
+      msm_scan_rounds_kernel<2><<<1, 1024, 0, st>>>(s->counts.as<unsigned>(), g.nb, g.task, s->offsets.as<unsigned>(), ro, s->task_off.as<unsigned>(), s->cursors.as<unsigned>());
+    else
+      msm_scan_rounds_kernel<3><<<1, 1024, 0, st>>>(s->counts.as<unsigned>(), g.nb, g.task, s->offsets.as<unsigned>(), ro, s->task_off.as<unsigned>(), s->cursors.as<unsigned>());
+  }
   PLK_LAUNCHED();
 }
 
@@ -679,9 +733,7 @@ void execute_one(plk_msm_table* t, plk_msm_scratch* s, const void* d_scalars, vo
     msm_colsum_kernel<<<(g.nb + 255) / 256, 256, 0, st>>>(s->cta_hist.as<unsigned>(), g.nb, rows, s->counts.as<unsigned>());
     PLK_LAUNCHED();
     s->timer.mark(st);
-    msm_scan_kernel<<<1, 1024, 0, st>>>(s->counts.as<unsigned>(), g.nb, g.task, s->offsets.as<unsigned>(), s->task_off.as<unsigned>(),
-                                        s->cursors.as<unsigned>());
-    PLK_LAUNCHED();
+    launch_scan(s, g, st);
     s->timer.mark(st);
     msm_scatter_smem_kernel<C><<<rows, 1024, smem, st>>>(reinterpret_cast<const uint4*>(d_scalars), g, chunk, s->cta_hist.as<unsigned>(),
                                                          s->offsets.as<unsigned>(), s->sorted.as<unsigned>());
@@ -693,9 +745,7 @@ void execute_one(plk_msm_table* t, plk_msm_scratch* s, const void* d_scalars, vo
     msm_count_kernel<C><<<sblocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(d_scalars), g, s->counts.as<unsigned>());
     PLK_LAUNCHED();
     s->timer.mark(st);
-    msm_scan_kernel<<<1, 1024, 0, st>>>(s->counts.as<unsigned>(), g.nb, g.task, s->offsets.as<unsigned>(), s->task_off.as<unsigned>(),
-                                        s->cursors.as<unsigned>());
-    PLK_LAUNCHED();
+    launch_scan(s, g, st);
     s->timer.mark(st);
     msm_scatter_kernel<C><<<sblocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(d_scalars), g, s->cursors.as<unsigned>(),
                                                    s->sorted.as<unsigned>());
@@ -703,9 +753,39 @@ void execute_one(plk_msm_table* t, plk_msm_scratch* s, const void* d_scalars, vo
     s->timer.mark(st);
   }
   const unsigned ablocks = (unsigned)((t->max_tasks + kAccThreads - 1) / kAccThreads);
-  msm_accumulate_kernel<C><<<ablocks, kAccThreads, 0, st>>>(t->table.p, s->sorted.as<unsigned>(), s->offsets.as<unsigned>(),
-                                                            s->task_off.as<unsigned>(), g.nb, g.task, s->partials.p);
-  PLK_LAUNCHED();
+  if (g.affine_rounds > 0) {
+    // batched-affine tree rounds (msm_affine.cuh), then the XYZZ task kernel over the shortened lists
+    const size_t entries = (size_t)g.n * g.nwin;
+    const char* pte = getenv("PLK_MSM_AFF_PER_THREAD");          // tuning knob
+    const int per_thread_env = pte ? atoi(pte) : 0;
+    const unsigned* in_off = s->offsets.as<unsigned>();
+    for (int r = 0; r < g.affine_rounds; ++r) {
+      const size_t bound = (entries >> (r + 1)) + g.nb + 1;                 // output slots of this round, upper bound
+      // ~2 waves of 3 resident CTAs per SM, between 16 and 64 slots per thread (fewer slots: the shared inversion
+      // amortises worse; more: too few CTAs to cover each other's inversion stall)
+      size_t per = bound / ((size_t)148 * 3 * kAffThreads * 2);
+      if (per < 16) per = 16;
+      if (per > 64) per = 64;
+      if (per_thread_env >= 1 && per_thread_env <= 4096) per = per_thread_env;
+      const unsigned ctas = (unsigned)((bound + kAffThreads * per - 1) / (kAffThreads * per));
+      unsigned* out_off = s->aff_off[r].as<unsigned>();
+      if (r == 0)
+        msm_affine_round_kernel<C, true><<<ctas, kAffThreads, 0, st>>>(t->table.p, s->sorted.as<unsigned>(), nullptr, in_off, out_off, g.nb,
+                                                                       (unsigned)per, s->aff_prefix.p, s->aff[0].p);
+      else
+        msm_affine_round_kernel<C, false><<<ctas, kAffThreads, 0, st>>>(nullptr, nullptr, s->aff[(r - 1) & 1].p, in_off, out_off, g.nb,
+                                                                        (unsigned)per, s->aff_prefix.p, s->aff[r & 1].p);
+      PLK_LAUNCHED();
+      in_off = out_off;
+    }
+    msm_accumulate_points_kernel<C><<<ablocks, kAccThreads, 0, st>>>(s->aff[(g.affine_rounds - 1) & 1].p, in_off, s->task_off.as<unsigned>(), g.nb,
+                                                                     g.task, s->partials.p);
+    PLK_LAUNCHED();
+  } else {
+    msm_accumulate_kernel<C><<<ablocks, kAccThreads, 0, st>>>(t->table.p, s->sorted.as<unsigned>(), s->offsets.as<unsigned>(),
+                                                              s->task_off.as<unsigned>(), g.nb, g.task, s->partials.p);
+    PLK_LAUNCHED();
+  }
   s->timer.mark(st);
   msm_bucket_sum_kernel<C><<<(2 * g.nb + 127) / 128, 128, 0, st>>>(s->partials.p, s->task_off.as<unsigned>(), g.nb, s->buckets.p,
                                                                s->big_list.as<unsigned>());
@@ -798,9 +878,24 @@ void curve_mul(const void* d_points_xy, const void* d_scalars, size_t n, void* d
 }
 
 template <class C>
+void commit_blind(const void* d_msm_xyz, const unsigned char* d_msm_zero, const void* d_blinding, const uint64_t* h_xy, bool h_zero, size_t k,
+                  void* d_out_xy, unsigned char* d_out_zero, cudaStream_t st) {
+  typedef Fp<typename C::Base> F;
+  if (k == 0) return;
+  Affine<C> h = Affine<C>::identity();
+  if (!h_zero && h_xy) {
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(h_xy);
+    for (int i = 0; i < F::N; ++i) { h.x.l[i] = p[i]; h.y.l[i] = p[F::N + i]; }
+  }
+  commit_blind_kernel<C><<<(unsigned)((k + 63) / 64), 64, 0, st>>>(reinterpret_cast<const uint32_t*>(d_msm_xyz), d_msm_zero, d_blinding, h, k,
+                                                                 d_out_xy, d_out_zero);
+  PLK_LAUNCHED();
+}
+
+template <class C>
 const MsmOps* make_msm_ops() {
   static const MsmOps ops = {&table_build<C>, &import_points<C>, &execute_one<C>, &combine_partials<C>, &generate_points<C>,
-                             &to_affine_batch<C>, &multisum<C>, &curve_mul<C>};
+                             &to_affine_batch<C>, &multisum<C>, &curve_mul<C>, &commit_blind<C>};
   return &ops;
 }
 }  // namespace plk

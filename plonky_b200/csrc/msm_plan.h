@@ -11,6 +11,7 @@ constexpr int kRangeSize = 8;        // buckets per running-sum range
 constexpr int kAccThreads = 128;
 constexpr int kQuadThreads = 64;     // CTA size of the quad-cooperative tail kernels (16 quads)
 constexpr int kFinalQuadsMax = 64;   // quads of the single-CTA final reduction
+constexpr int kAffineRoundsHostMax = 3;  // = kAffineRoundsMax of msm_affine.cuh
 constexpr unsigned kSortMaxBins = 32768;   // shared-memory histogram sort: nb * 4 B <= 128 KiB
 
 struct MsmGeom {
@@ -21,6 +22,7 @@ struct MsmGeom {
   unsigned nbw;             // buckets per window = 2^(c-1)
   int variable;             // 1: no table of powers, buckets per window, windows combined with doublings (msm_parallel)
   unsigned task;            // S: entries per accumulate task (power of two, <= kTaskSizeMax)
+  int affine_rounds;        // batched-affine tree rounds before the XYZZ task kernel (0 = none)
 };
 
 }  // namespace plk
@@ -31,6 +33,9 @@ struct MsmGeom {
 struct plk_msm_scratch {
   plk::DevBuf counts, offsets, task_off, cursors, sorted, partials, buckets, ranges, big_list;   // big_list[0] = count
   plk::DevBuf cta_hist;    // sort_rows x nb per-CTA histograms / column prefixes (shared-memory sort)
+  // batched-affine rounds (msm_affine.cuh): ping-pong point lists, the parked running products, per-round bucket offsets
+  plk::DevBuf aff[2], aff_prefix, aff_off[3];
+  int affine_rounds = 0;   // 0 = XYZZ accumulation straight from the table
   unsigned sort_rows = 0;  // CTAs of the shared-memory sort; 0 = global-atomic counting sort
   plk::PhaseTimer timer;   // count | scan | scatter | accumulate | bucket_sum | range | final
 };
@@ -74,6 +79,8 @@ struct MsmOps {
   void (*multisum)(const void* d_points, const unsigned char* d_zero, const unsigned long long* d_offsets, size_t lists, void* d_out_xyz,
                    unsigned char* d_out_zero, cudaStream_t st);
   void (*curve_mul)(const void* d_points_xy, const void* d_scalars, size_t n, void* d_out_xyz, unsigned char* d_out_zero, cudaStream_t st);
+  void (*commit_blind)(const void* d_msm_xyz, const unsigned char* d_msm_zero, const void* d_blinding, const uint64_t* h_xy, bool h_zero, size_t k,
+                       void* d_out_xy, unsigned char* d_out_zero, cudaStream_t st);
 };
 // msm_parallel on device buffers (variable base, no table of powers; src/curve/curve_msm.rs:54-61): n affine points
 // (identity = (0, 0)) and n Montgomery scalars -> one normalised point (3*L u64) + zero flag, asynchronous on `st`.

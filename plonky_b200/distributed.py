@@ -170,6 +170,7 @@ class DistributedNtt:
         self.L = FL[field]
         self.rows = (1 << log_r1) // self.world
         self.cols = (1 << self.log_m) // self.world
+        self.exchange_kind = "NCCL all_to_all_single" if self.world > 1 else "local copy"
         self.plan_m = fft_precompute(field, 1 << self.log_m)
         self.plan_n = fft_precompute(field, 1 << log_n)
         shape_in = (self.rows, 1 << self.log_m, self.L)
@@ -199,6 +200,25 @@ class DistributedNtt:
         else:
             dist.all_to_all_single(self.recv.view(-1), self.send.view(-1), group=self.group)
         return self.phase_b(self.recv, inverse)
+
+    def check_against_single_gpu(self, local_rows: torch.Tensor, inverse: bool = False) -> bool:
+        """Untimed self-check (bench.py): gather every rank's rows, run the single-GPU transform of the whole vector on
+        this rank and compare this rank's output slice word for word.  -> AND over the ranks."""
+        out = self.forward(local_rows, inverse).clone()
+        R1, M = 1 << self.log_r1, 1 << self.log_m
+        if self.world > 1:
+            full = torch.empty((R1, M, self.L), dtype=torch.int64, device="cuda")
+            dist.all_gather_into_tensor(full.view(-1), local_rows.contiguous().view(-1), group=self.group)
+        else:
+            full = local_rows
+        x = full.permute(1, 0, 2).contiguous().view(R1 * M, self.L)           # x[j_1 + R1 j'] = rows[j_1][j']
+        want = torch.empty_like(x)
+        fft_dev(self.plan_n, x, want, inverse=inverse)
+        mine = want.view(R1, M, self.L)[:, self.rank * self.cols:(self.rank + 1) * self.cols].contiguous()
+        ok = torch.tensor([1 if torch.equal(out, mine) else 0], dtype=torch.int64, device="cuda")
+        if self.world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        return bool(ok.item())
 
     # ---- layout helpers (host-side, for tests and for callers that start from natural order) ----
     def input_rows(self, x_natural: torch.Tensor, rank: int = None) -> torch.Tensor:

@@ -14,157 +14,254 @@
     group 4   1 x MSM(n)   [PI quotient]                     plonk.rs:231
 Totals: 18 MSM(n), 19 (I)FFT(n), 13 (I)FFT(8n) per proof (the remaining 8n transforms sit in the PI
 quotient's polynomial arithmetic; they are replayed as plain FFT(8n)).  The full prover cannot run here
-(Rust + an #[ignore]d test); this replays only the device work of the path, data resident,
-with the reference's dependency groups as barriers.  Multi-GPU = replicas: the independent items of a
-group are dealt round-robin to the ranks (no data-path collective); commitments are all-gathered.
+(Rust + an #[ignore]d test); this replays only the device work of the path with the
+reference's dependency groups as barriers: the wire values arrive from HOST memory (H2D inside the timed
+region) and every group ends with the D2H read of its commitments (what the Fiat-Shamir challenger needs
+before the next group can start).  Multi-GPU = replicas: the independent items of a group are dealt
+round-robin to the ranks (no data-path collective); commitments are all-gathered.
 
   python tools/prover_mix.py [--log-n 16] [--reps 5]
   python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/prover_mix.py
+bench.py imports `bench()` for its `prover_mix` sub-object.
 """
 import argparse
 import json
 import os
 import sys
-
-import numpy as np
-import torch
-import torch.distributed as dist
+import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import plonky_b200 as pk  # noqa: E402
-from plonky_b200 import distributed as pkd  # noqa: E402
+
+
+class Mix:
+    def __init__(self, cx, log_n):
+        torch, np, pk, pkd = cx.torch, cx.np, cx.pk, cx.pkd
+        self.cx = cx
+        self.n = n = 1 << log_n
+        self.world, self.rank = cx.world, cx.rank
+        self.curve, self.field = pk.TWEEDLEDEE, pk.TWEEDLEDUM_BASE          # Circuit<Tweedledee>: scalars live in TweedledumBase
+        self.pts = pkd.pedersen_generators_dev(self.curve, 0, n)             # same generators on every rank (replicated table)
+        self.table = pkd.msm_precompute_affine_dev(self.curve, self.pts, 11)
+        self.plan_n = pk.fft_precompute(self.field, n)
+        self.plan_8n = pk.fft_precompute(self.field, 8 * n)
+        rng = np.random.Generator(np.random.PCG64(5))
+        a = rng.integers(0, 1 << 62, size=(9, n, 4), dtype=np.uint64)
+        self.vals_h = torch.from_numpy(a.view(np.int64)).pin_memory()        # Witness wire values, host
+        self.vals = torch.empty((9, n, 4), dtype=torch.int64, device="cuda")
+        self.buf_n = torch.zeros_like(self.vals)
+        self.buf_8n = torch.zeros((9, 8 * n, 4), dtype=torch.int64, device="cuda")
+        self.outs = torch.zeros((18, 3, 4), dtype=torch.int64, device="cuda")
+        self.zeros = torch.zeros((18, 8), dtype=torch.uint8, device="cuda")
+        self.zbytes = torch.zeros(32, dtype=torch.uint8, device="cuda")
+        self.gathered = torch.zeros((self.world, 18, 3, 4), dtype=torch.int64, device="cuda")
+        self.outs_h = torch.zeros((18, 3, 4), dtype=torch.int64).pin_memory()
+        self.h2d_bytes = self.vals_h.numel() * 8
+
+    def mine(self, k):
+        return [i for i in range(k) if i % self.world == self.rank]
+
+    def group_end(self, lo, hi):
+        """dependency barrier: the group's commitments reach the host (rank 0 holds all of them for N > 1)"""
+        cx = self.cx
+        if self.world > 1:
+            cx.dist.all_gather_into_tensor(self.gathered.view(-1), self.outs.view(-1))
+        self.outs_h[lo:hi].copy_(self.outs[lo:hi], non_blocking=True)
+        cx.torch.cuda.current_stream().synchronize()
+
+    def proof(self, single=False):
+        """one proof's device work; single=True forces the one-GPU batched path (the N > 1 self-check)"""
+        pkd = self.cx.pkd
+        n = self.n
+        world = 1 if single else self.world
+        t, pn, p8 = self.table, self.plan_n, self.plan_8n
+        self.vals.copy_(self.vals_h, non_blocking=True)
+        # group 1
+        if world == 1:
+            # one batched launch sequence per kind, like values_to_polynomials / commit_polynomials
+            pkd.fft_dev(pn, self.vals, self.buf_n, inverse=True)
+            pkd.fft_dev(p8, self.buf_n, self.buf_8n)
+            pkd.msm_execute_batch_dev(t, self.buf_n, self.outs[:9], self.zbytes[:9])
+            pkd.fft_dev(pn, self.vals, self.buf_n, inverse=True)
+        else:
+            for i in self.mine(9):
+                pkd.fft_dev(pn, self.vals[i], self.buf_n[i], inverse=True)
+                pkd.fft_dev(p8, self.buf_n[i], self.buf_8n[i])
+                pkd.msm_execute_dev(t, self.buf_n[i], self.outs[i], self.zeros[i])
+                pkd.fft_dev(pn, self.vals[i], self.buf_n[i], inverse=True)
+        if not single:
+            self.group_end(0, 9)
+        # group 2 (Z): every rank keeps its own copy of the chain input so that group 3 can be dealt out
+        pkd.fft_dev(pn, self.vals[0], self.buf_n[0], inverse=True)
+        if world == 1 or self.rank == 0:
+            pkd.msm_execute_dev(t, self.buf_n[0], self.outs[9], self.zeros[9])
+        if not single:
+            self.group_end(9, 10)
+        # group 3: FFT(8n), IFFT(8n), divide_by_z_h's coset pair -- a chain, replicated on every rank
+        pkd.fft_dev(p8, self.buf_n[0], self.buf_8n[0])
+        pkd.fft_dev(p8, self.buf_8n[0], self.buf_8n[1], inverse=True)
+        pkd.fft_dev(p8, self.buf_8n[1], self.buf_8n[2], coset=True)
+        pkd.fft_dev(p8, self.buf_8n[2], self.buf_8n[3], inverse=True, coset=True)
+        if world == 1:
+            # t chunks: dense scalars (the 8n evaluations of the chain's first transform stand in for the quotient's chunks)
+            pkd.msm_execute_batch_dev(t, self.buf_8n[0, :7 * n].view(7, n, 4), self.outs[10:17], self.zbytes[10:17])
+        else:
+            for i in self.mine(7):
+                pkd.msm_execute_dev(t, self.buf_8n[0, i * n:(i + 1) * n], self.outs[10 + i], self.zeros[10 + i])
+        for i in (range(8) if world == 1 else self.mine(8)):     # the remaining 8n transforms of the quotient arithmetic
+            pkd.fft_dev(p8, self.buf_8n[4 + i % 5], self.buf_8n[4 + (i + 1) % 5], inverse=bool(i & 1))
+        if not single:
+            self.group_end(10, 17)
+        # group 4
+        if world == 1 or self.rank == 0:
+            pkd.msm_execute_dev(t, self.buf_n[0], self.outs[17], self.zeros[17])
+        if not single:
+            self.group_end(17, 18)
+
+    def commitments(self):
+        """(18, 3, 4) uint64 on the host: for N > 1 item i comes from the rank that owns it"""
+        np = self.cx.np
+        self.cx.torch.cuda.synchronize()
+        if self.world == 1:
+            return self.outs.cpu().numpy().view(np.uint64).copy()
+        g = self.gathered.cpu().numpy().view(np.uint64)
+        own = [i % self.world for i in range(9)] + [0] + [i % self.world for i in range(7)] + [0]
+        return np.stack([g[own[i], i] for i in range(18)])
+
+
+def bench(cx, log_n=16, reps=5, with_cpu=False):
+    torch, np, pk = cx.torch, cx.np, cx.pk
+    m = Mix(cx, log_n)
+    for _ in range(2):
+        m.proof()
+    cx.barrier()
+    l0 = pk.kernel_launch_count()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        m.proof()
+    cx.barrier()
+    ms = cx.max_over_ranks((time.perf_counter() - t0) * 1e3 / reps)
+    launches = (pk.kernel_launch_count() - l0) // reps
+    got = m.commitments()
+    checks = []
+    # (1) the chain FFT(8n) -> IFFT(8n) -> coset LDE -> coset IFFT is the identity on the zero-padded coefficients
+    n = m.n
+    ok = bool(torch.equal(m.buf_8n[3, :n], m.buf_n[0])) and not bool(m.buf_8n[3, n:].any())
+    checks.append("8n transform chain (FFT, IFFT, coset LDE, coset IFFT) returns the zero-padded coefficients bit for bit")
+    # (2) N > 1: the replica-distributed commitments equal the single-GPU batched path on rank 0's GPU
+    if cx.world > 1:
+        m.proof(single=True)
+        torch.cuda.synchronize()
+        alone = m.outs.cpu().numpy().view(np.uint64)
+        same = bool(np.array_equal(alone, got))
+        t = torch.tensor([1 if (same and ok) else 0], dtype=torch.int64, device="cuda")
+        cx.dist.all_reduce(t, op=cx.dist.ReduceOp.MIN)
+        ok = bool(t.item())
+        checks.append("the 18 commitments gathered from the ranks == the single-GPU batched path recomputed on every rank")
+    res = {"workload": f"prover L1 call mix, n = 2^{log_n} gates (18 MSM(n), 19 FFT(n), 13 FFT(8n)), wire values from host memory, "
+                       "one D2H of the commitments per dependency group",
+           "n_gpus": cx.world, "ms_per_proof_mix": ms, "proofs_per_sec": 1e3 / ms,
+           "mode": "replicas, round-robin within dependency groups" if cx.world > 1 else "single GPU, batched launches",
+           "h2d_bytes_per_proof": m.h2d_bytes, "d2h_bytes_per_proof": 18 * 3 * 4 * 8, "timing": "host wall clock, barrier + synchronize on both sides, max over ranks",
+           "launches_per_proof_rank0": int(launches)}
+    # (3) N = 1: the CPU restatement of the reference on the same inputs -- parity of every commitment and the CPU time of the mix
+    if with_cpu and cx.rank == 0 and cx.world == 1:
+        cpu = cpu_mix(cx, m, got)
+        ok = ok and cpu.pop("ok")
+        checks.append("all 18 commitments and the 9 IFFT(n) outputs == the CPU restatement (msm_execute_parallel w=11, ifft) on the same inputs")
+        res["cpu_baseline"] = cpu
+    res["verified"] = ok
+    res["verification"] = checks
+    m.table.close()
+    return res
+
+
+def cpu_mix(cx, m, got):
+    """The same call mix through oracle/ref_port.cpp on the host cores (bench.py's cpu_baseline leg): timing + parity."""
+    np = cx.np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_port as rp
+    try:
+        rp.build(native=True)
+        L = rp.lib(native=True)
+    except Exception:
+        L = rp.lib()
+    cores = os.cpu_count() or 1
+    L.ref_set_threads(cores)
+    n = m.n
+    vals = m.vals_h.numpy().view(np.uint64)
+    gens = m.pts.cpu().numpy().view(np.uint64)
+    table = rp.MsmTable(m.curve, gens, None, 11, L)
+    pn, p8 = rp.FftPlan(m.field, n, L), rp.FftPlan(m.field, 8 * n, L)
+    t0 = time.perf_counter()
+    coeffs = [pn.run(vals[i], inverse=True) for i in range(9)]
+    pad = np.zeros((8 * n, 4), dtype=np.uint64)
+    for i in range(9):
+        pad[:n] = coeffs[i]
+        p8.run(pad)
+    commits = [table.execute(coeffs[i], parallel=True) for i in range(9)]
+    for i in range(9):
+        pn.run(vals[i], inverse=True)
+    commits.append(table.execute(coeffs[0], parallel=True))
+    pn.run(vals[0], inverse=True)
+    pad[:n] = coeffs[0]
+    x0 = p8.run(pad)
+    x = x0
+    for k in range(3 + 8):                     # the chain's other 8n transforms + the quotient arithmetic's
+        x = p8.run(x, inverse=bool(k & 1))
+    commits += [table.execute(x0[i * n:(i + 1) * n], parallel=True) for i in range(7)]
+    commits.append(table.execute(coeffs[0], parallel=True))
+    cpu_ms = (time.perf_counter() - t0) * 1e3
+    ok = True
+    for i, (xy, z) in enumerate(commits):
+        ok = ok and (z == (not got[i].any())) and (z or bool(np.array_equal(got[i][:2], xy)))
+    dev_coeffs = m.buf_n.cpu().numpy().view(np.uint64)
+    # buf_n holds the second IFFT(n) batch of group 1 (row 0 is overwritten identically by group 2)
+    ok = ok and all(bool(np.array_equal(dev_coeffs[i], coeffs[i])) for i in range(9))
+    return {"ok": ok, "value": cpu_ms, "unit": "ms per proof mix", "cores": cores, "kind": "port",
+            "sample": "the same 18 MSM(n) + 19 (I)FFT(n) + 13 (I)FFT(8n) through the C++ restatement, one run, table and plans untimed"}
 
 
 def main():
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import plonky_b200 as pk
+    from plonky_b200 import distributed as pkd
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--log-n", type=int, default=16)
     ap.add_argument("--reps", type=int, default=5)
-    ap.add_argument("--ipa", action="store_true", help="also time the Halo IPA rounds (halo.rs:63-124) on rank 0")
     args = ap.parse_args()
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
+
+    class Cx:
+        pass
+    cx = Cx()
+    cx.np, cx.torch, cx.dist, cx.pk, cx.pkd = np, torch, dist, pk, pkd
+    cx.world = int(os.environ.get("WORLD_SIZE", "1"))
+    cx.rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     pk._check(pk.lib().plk_set_device(local))
-    if world > 1:
+    if cx.world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    n = 1 << args.log_n
-    curve, field = pk.TWEEDLEDEE, pk.TWEEDLEDUM_BASE          # Circuit<Tweedledee>: scalars live in TweedledumBase
-    pts = pkd.points_generate_dev(curve, 77, n)                # same generators on every rank (replicated table)
-    table = pkd.msm_precompute_affine_dev(curve, pts, 11)
-    plan_n = pk.fft_precompute(field, n)
-    plan_8n = pk.fft_precompute(field, 8 * n)
-    rng = np.random.Generator(np.random.PCG64(5))
-    def rnd(rows, m):
-        a = rng.integers(0, 1 << 62, size=(rows, m, 4), dtype=np.uint64)
-        return torch.from_numpy(a.view(np.int64)).cuda()
-    vals = rnd(9, n)
-    buf_n = torch.empty_like(vals)
-    buf_8n = torch.empty((9, 8 * n, 4), dtype=torch.int64, device="cuda")
-    outs = torch.zeros((18, 3, 4), dtype=torch.int64, device="cuda")
-    zeros = torch.zeros((18, 8), dtype=torch.uint8, device="cuda")
-    zbytes = torch.zeros(32, dtype=torch.uint8, device="cuda")
-    gathered = torch.zeros((world, 18, 3, 4), dtype=torch.int64, device="cuda")
 
-    def mine(k):                       # items of a k-item group owned by this rank
-        return [i for i in range(k) if i % world == rank]
-
-    def proof():
-        # group 1
-        my = mine(9)
-        if world == 1:
-            # one batched launch sequence per kind, like values_to_polynomials / commit_polynomials
-            pkd.fft_dev(plan_n, vals, buf_n, inverse=True)
-            pkd.fft_dev(plan_8n, buf_n, buf_8n)
-            pkd.msm_execute_batch_dev(table, buf_n, outs[:9], zbytes[:9])
-            pkd.fft_dev(plan_n, vals, buf_n, inverse=True)
-        else:
-            for i in my:
-                pkd.fft_dev(plan_n, vals[i], buf_n[i], inverse=True)
-                pkd.fft_dev(plan_8n, buf_n[i], buf_8n[i])
-                pkd.msm_execute_dev(table, buf_n[i], outs[i], zeros[i])
-                pkd.fft_dev(plan_n, vals[i], buf_n[i], inverse=True)
-        sync()
-        # group 2
-        if rank == 0:
-            pkd.fft_dev(plan_n, vals[0], buf_n[0], inverse=True)
-            pkd.msm_execute_dev(table, buf_n[0], outs[9], zeros[9])
-        sync()
-        # group 3
-        if rank == 0:
-            pkd.fft_dev(plan_8n, buf_n[0], buf_8n[0])
-            pkd.fft_dev(plan_8n, buf_8n[0], buf_8n[1], inverse=True)
-            pkd.fft_dev(plan_8n, buf_8n[1], buf_8n[2], coset=True)
-            pkd.fft_dev(plan_8n, buf_8n[2], buf_8n[3], inverse=True, coset=True)
-        sync()
-        if world == 1:
-            pkd.msm_execute_batch_dev(table, buf_8n[3, :7 * n].view(7, n, 4), outs[10:17], zbytes[10:17])
-        else:
-            for i in mine(7):
-                pkd.msm_execute_dev(table, buf_8n[3, i * n:(i + 1) * n], outs[10 + i], zeros[10 + i])
-        for i in mine(8):              # the remaining 8n transforms of the quotient arithmetic
-            pkd.fft_dev(plan_8n, buf_8n[i], buf_8n[(i + 1) % 9], inverse=bool(i & 1))
-        sync()
-        # group 4
-        if rank == 0:
-            pkd.msm_execute_dev(table, buf_n[1], outs[17], zeros[17])
-        if world > 1:
-            dist.all_gather_into_tensor(gathered.view(-1), outs.view(-1))
-
-    def sync():
-        if world > 1:
+    def barrier():
+        if cx.world > 1:
             dist.barrier()
+        torch.cuda.synchronize()
 
-    for _ in range(2):
-        proof()
-    torch.cuda.synchronize()
-    sync()
-    l0 = pk.kernel_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.reps):
-        proof()
-    e1.record()
-    torch.cuda.synchronize()
-    sync()
-    t = torch.tensor([e0.elapsed_time(e1) / args.reps], dtype=torch.float64, device="cuda")
-    if world > 1:
+    def max_over_ranks(ms):
+        if cx.world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ipa = None
-    if args.ipa and rank == 0:
-        # batch_opening_proof's loop (halo.rs:63-124): log2(n) rounds of 2 variable-base MSMs + 2 inner products,
-        # then the fold of a, b and G; vectors stay on the device, one challenge per round comes from the host
-        import time
-        a = rng.integers(0, 1 << 62, size=(n, 4), dtype=np.uint64)
-        b = rng.integers(0, 1 << 62, size=(n, 4), dtype=np.uint64)
-        g = pk.points_generate(curve, 77, n)
-        u = rng.integers(1, 1 << 62, size=4, dtype=np.uint64)
-        u_inv = pk.field_op(field, "inverse", u.reshape(1, 4))[0]
-        host_table = pk.msm_precompute_affine(curve, g, 11)
-
-        def run(table_mode):
-            best = None
-            for _ in range(3):
-                st = pk.HaloIpaRounds(curve, a, b, precomputation=host_table) if table_mode else pk.HaloIpaRounds(curve, a, b, g)
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                while len(st) > 1:
-                    st.round_lr()
-                    st.fold(u, u_inv)
-                st.read()                         # halo_a[0], halo_b[0], halo_g[0].to_affine()
-                dt = (time.perf_counter() - t0) * 1e3
-                best = dt if best is None else min(best, dt)
-                st.close()
-            return best
-
-        ipa = {"rounds": args.log_n, "ms_all_rounds_table_mode": run(True), "ms_all_rounds_folding_mode": run(False),
-               "timing": "host wall clock around the synchronous C-ABI calls (2 per round + final read), best of 3"}
-    if rank == 0:
-        print(json.dumps({"ipa": ipa, "workload": f"prover L1 call mix, n = 2^{args.log_n} gates (18 MSM(n), 19 FFT(n), 13 FFT(8n))",
-                          "n_gpus": world, "ms_per_proof_mix": float(t.item()), "mode": "replicas, round-robin within dependency groups",
-                          "launches_per_proof_rank0": (pk.kernel_launch_count() - l0) // args.reps}))
-    if world > 1:
+        return float(t.item())
+    cx.barrier, cx.max_over_ranks = barrier, max_over_ranks
+    res = bench(cx, args.log_n, args.reps, with_cpu=(cx.world == 1))
+    if cx.rank == 0:
+        print(json.dumps(res))
+    if cx.world > 1:
         dist.destroy_process_group()
 
 
