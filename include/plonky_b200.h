@@ -200,6 +200,35 @@ int plk_permutation_polynomial(int field, size_t degree, unsigned num_routed, co
                                size_t sigma_row_len, size_t sigma_stride, const uint64_t* k_is,
                                const uint64_t* beta, const uint64_t* gamma, uint64_t* out);
 
+/* Circuit::vanishing_poly (src/plonk.rs:375-456) for a 4-limb scalar field: the pointwise part (plk_vanishing_points*)
+ * and the whole function (plk_vanishing_poly).  m = 8 * degree points x_i = w_8n^i; row-major inputs:
+ *   wires_8n      9 rows (NUM_WIRES) of m evaluations, constants_8n 6 rows (NUM_CONSTANTS), sigma_8n 6 rows (NUM_ROUTED_WIRES),
+ *   z_8n          m evaluations of Plonk's Z, subgroup_8n the m points (plk_fft_subgroup of the 8n plan),
+ *   k_is          the 6 routed shifts get_subgroup_shift(j) (seeded ChaCha RNG in the reference: caller-supplied),
+ *   alpha, beta, gamma the challenges; inner_zeta, inner_a = InnerC::ZETA and InnerC::A of the recursion's inner curve
+ *   (InnerC::BaseField = this field; curve_endo.rs:55, curve_dbl.rs:45).
+ * out_8n[i] = reduce_with_powers([L_1(x)(Z(x) - 1), Z(x) f'(x) - g'(x) Z(g x)] ++ evaluate_all_constraints(...), alpha)
+ * with evaluate_all_constraints = src/gates/mod.rs:46-125 over the ten gates of src/gates/.  "right" is the point 8 steps
+ * on, "below" 8 * GRID_WIDTH (65) steps on (plonk.rs:407-409).  d_params (device variant): k_is[6], alpha, beta, gamma,
+ * inner_zeta, inner_a as 11 consecutive elements. */
+int plk_vanishing_points(int field, size_t degree, const uint64_t* wires_8n, const uint64_t* constants_8n,
+                         const uint64_t* sigma_8n, const uint64_t* z_8n, const uint64_t* subgroup_8n,
+                         const uint64_t* k_is, const uint64_t* alpha, const uint64_t* beta, const uint64_t* gamma,
+                         const uint64_t* inner_zeta, const uint64_t* inner_a, uint64_t* out_8n);
+int plk_vanishing_points_dev(int field, size_t degree, const void* d_wires_8n, const void* d_constants_8n,
+                             const void* d_sigma_8n, const void* d_z_8n, const void* d_subgroup_8n,
+                             const void* d_params, void* d_out_8n, void* stream);
+/* The whole of vanishing_poly against fft_precomputation_8n: pad_to_8n + FFT of the n Z coefficients (plonk.rs:388-391),
+ * the pointwise evaluation, Polynomial::from_evaluations (plonk.rs:455) -- 8n coefficients out, nothing leaves the device
+ * in between.  PLK_ESIZE unless the plan has size 8 * degree. */
+int plk_vanishing_poly(const plk_fft_plan* plan_8n, size_t degree, const uint64_t* wires_8n,
+                       const uint64_t* constants_8n, const uint64_t* sigma_8n, const uint64_t* plonk_z_coeffs,
+                       const uint64_t* k_is, const uint64_t* alpha, const uint64_t* beta, const uint64_t* gamma,
+                       const uint64_t* inner_zeta, const uint64_t* inner_a, uint64_t* out_coeffs_8n);
+/* w^k for k < size: the plan's evaluation domain in natural order (Field::cyclic_subgroup_known_order,
+ * src/field/field.rs:292-300; subgroup_n / subgroup_8n of Circuit, src/plonk.rs:47-51). */
+int plk_fft_subgroup(const plk_fft_plan* p, uint64_t* out);
+
 /* Device-resident variants: d_in / d_out hold n_in resp. `size` elements per row, k rows.
  * flags: bit0 inverse, bit1 coset shift by the field generator on the coefficient side. */
 #define PLK_FFT_INVERSE 1u

@@ -701,3 +701,143 @@ def field_test_inputs(modulus: int, word_bits: int = 64) -> List[int]:
     diff_mod = [modulus - x for x in basic if x < modulus and x != 0]
     basics = [x for x in basic if x < modulus]
     return basics + diff_max + diff_mod
+
+
+# ---------------------------------------------------------------------------------------------
+# src/plonk.rs:375-456 vanishing_poly (the pointwise part) with src/gates/mod.rs:46-125 evaluate_all_constraints and the
+# ten gates' evaluate_unfiltered (src/gates/*.rs), src/plonk_util.rs:7-33 (eval_zero_poly, eval_l_1, reduce_with_powers),
+# src/mds.rs:63-77 (Cauchy MDS matrix).  Canonical integers mod p throughout.
+# ---------------------------------------------------------------------------------------------
+NUM_WIRES, NUM_ROUTED_WIRES, NUM_CONSTANTS, GRID_WIDTH, RESCUE_SPONGE_WIDTH = 9, 6, 6, 65, 4
+NUM_ADVICE_WIRES = NUM_WIRES - NUM_ROUTED_WIRES
+GATE_PREFIXES = {                       # src/gates/*.rs `const PREFIX`
+    "curve_add": (1, 0, 1, 0, 1), "curve_dbl": (1, 0, 1, 1, 1), "curve_endo": (1, 1), "base_4_sum": (1, 0, 0, 0),
+    "public_input": (1, 0, 1, 0, 0, 1), "buffer": (1, 0, 1, 0, 0, 0), "constant": (1, 0, 1, 1, 0), "arithmetic": (1, 0, 0, 1),
+    "rescue_a": (0, 0), "rescue_b": (0, 1),
+}
+GATE_ORDER = ("curve_add", "curve_dbl", "curve_endo", "base_4_sum", "public_input", "buffer", "constant", "arithmetic",
+              "rescue_a", "rescue_b")               # the order of evaluate_all_constraints, gates/mod.rs:52-113
+
+
+def mds_matrix(field: Field, n: int = RESCUE_SPONGE_WIDTH) -> List[List[int]]:
+    """mds.rs:63-77: Cauchy matrix 1 / (x_r - y_c), x_r = n + r, y_c = c."""
+    return [[field.inv((n + r - c) % field.p) for c in range(n)] for r in range(n)]
+
+
+def eval_l_1(field: Field, n: int, x: int) -> int:
+    """plonk_util.rs:14-24"""
+    p = field.p
+    if x == 1:
+        return 1
+    return (pow(x, n, p) - 1) * field.inv(n * (x - 1) % p) % p
+
+
+def reduce_with_powers(field: Field, terms: Sequence[int], alpha: int) -> int:
+    """plonk_util.rs:27-33"""
+    s = 0
+    for t in reversed(terms):
+        s = (s * alpha + t) % field.p
+    return s
+
+
+def gate_prefix_filter(field: Field, prefix, consts) -> int:
+    """gates/mod.rs:281-293"""
+    prod = 1
+    for i, bit in enumerate(prefix):
+        prod = prod * (consts[i] if bit else (1 - consts[i])) % field.p
+    return prod
+
+
+def gate_unfiltered(field: Field, name: str, consts, local, right, below, inner_zeta: int, inner_a: int) -> List[int]:
+    p = field.p
+    pl = len(GATE_PREFIXES[name])
+    if name == "curve_add":               # gates/curve_add.rs:38-81
+        x1, y1, so, sn, x2, y2, bit, inv, lam = local[:9]
+        x4, y4 = right[0], right[1]
+        x3 = (lam * lam - x1 - x2) % p
+        y3 = (lam * (x1 - x4) - y1) % p
+        nb = (1 - bit) % p
+        return [((y1 - y2) * inv - lam) % p, (bit * x3 + nb * x1 - x4) % p, (bit * y3 + nb * y1 - y4) % p,
+                (sn - (2 * so + bit)) % p, bit * nb % p, (inv * (x1 - x2) - 1) % p]
+    if name == "curve_dbl":               # gates/curve_dbl.rs:31-60
+        xo, yo, xn, yn, inv, lam = local[:6]
+        return [((3 * xo * xo + inner_a) * inv - lam) % p, (lam * lam - 2 * xo - xn) % p, (lam * (xo - xn) - yo - yn) % p,
+                (2 * yo * inv - 1) % p]
+    if name == "curve_endo":              # gates/curve_endo.rs:37-85
+        x1, y1, su_old, ss_old, x_in, y_in, b0, b1, inv = local[:9]
+        x3, y3 = right[0], right[1]
+        su_new, ss_new = below[2], below[3]
+        mult = ((inner_zeta - 1) * b1 + 1) % p
+        x2 = mult * x_in % p
+        y2 = (2 * b0 - 1) * y_in % p
+        lam = (y1 - y2) * inv % p
+        signed_limb = (2 * b0 - 1) * mult % p
+        return [(lam * lam - x1 - x2 - x3) % p, (lam * (x1 - x3) - y1 - y3) % p, (su_new - (4 * su_old + 2 * b1 + b0)) % p,
+                (ss_new - (2 * ss_old + signed_limb)) % p, b0 * (b0 - 1) % p, b1 * (b1 - 1) % p, (inv * (x1 - x2) - 1) % p]
+    if name == "base_4_sum":              # gates/base_4_sum.rs:36-62
+        acc = local[0]
+        limbs = local[2:9]
+        for l in limbs:
+            acc = (4 * acc + l) % p
+        out = [(acc - local[1]) % p]
+        for l in limbs:
+            out.append(l * (l - 1) * (l - 2) * (l - 3) % p)
+        return out
+    if name == "public_input":            # gates/public_input.rs:32-43
+        return [(local[NUM_ROUTED_WIRES + i] - right[i]) % p for i in range(NUM_ADVICE_WIRES)]
+    if name == "buffer":
+        return []
+    if name == "constant":                # gates/constant.rs:28-37
+        return [(consts[pl] - local[0]) % p]
+    if name == "arithmetic":              # gates/arithmetic.rs:35-49
+        return [(consts[pl] * local[0] * local[1] + consts[pl + 1] * local[2] - local[3]) % p]
+    mds = mds_matrix(field)
+    W = RESCUE_SPONGE_WIDTH
+    if name == "rescue_a":                # gates/rescue_a.rs:37-64
+        ins, roots, outs = local[:W], local[W:2 * W], right[:W]
+        out = []
+        for i in range(W):
+            out.append((pow(roots[i], 5, p) - ins[i]) % p)
+            out.append((consts[pl + i] + sum(mds[i][j] * roots[j] for j in range(W)) - outs[i]) % p)
+        return out
+    if name == "rescue_b":                # gates/rescue_b.rs:32-56
+        exps = [pow(v, 5, p) for v in local[:W]]
+        return [(consts[pl + i] + sum(mds[i][j] * exps[j] for j in range(W)) - right[i]) % p for i in range(W)]
+    raise KeyError(name)
+
+
+def evaluate_all_constraints(field: Field, consts, local, right, below, inner_zeta: int, inner_a: int) -> List[int]:
+    """gates/mod.rs:46-125: index-wise sum over the gates of filter * constraint."""
+    unified: List[int] = []
+    for name in GATE_ORDER:
+        f = gate_prefix_filter(field, GATE_PREFIXES[name], consts)
+        cs = gate_unfiltered(field, name, consts, local, right, below, inner_zeta, inner_a)
+        while len(unified) < len(cs):
+            unified.append(0)
+        for i, c in enumerate(cs):
+            unified[i] = (unified[i] + f * c) % field.p
+    return unified
+
+
+def vanishing_points(field: Field, degree: int, wires_8n, constants_8n, sigma_8n, z_8n, subgroup_8n, k_is, alpha: int, beta: int,
+                     gamma: int, inner_zeta: int, inner_a: int) -> List[int]:
+    """plonk.rs:393-452: the vanishing polynomial evaluated at the 8n points (before Polynomial::from_evaluations)."""
+    p = field.p
+    m = 8 * degree
+    out = []
+    for i, x in enumerate(subgroup_8n):
+        consts = [constants_8n[j][i] for j in range(NUM_CONSTANTS)]
+        ir, ib = (i + 8) % m, (i + 8 * GRID_WIDTH) % m
+        local = [wires_8n[j][i] for j in range(NUM_WIRES)]
+        right = [wires_8n[j][ir] for j in range(NUM_WIRES)]
+        below = [wires_8n[j][ib] for j in range(NUM_WIRES)]
+        terms = evaluate_all_constraints(field, consts, local, right, below, inner_zeta, inner_a)
+        z_x, z_gz = z_8n[i], z_8n[ir]
+        z1 = eval_l_1(field, degree, x) * (z_x - 1) % p
+        fp_, gp_ = 1, 1
+        for j in range(NUM_ROUTED_WIRES):
+            fp_ = fp_ * (local[j] + beta * (k_is[j] * x % p) + gamma) % p
+            gp_ = gp_ * (local[j] + beta * sigma_8n[j][i] + gamma) % p
+        shift = (fp_ * z_x - gp_ * z_gz) % p
+        out.append(reduce_with_powers(field, [z1, shift] + terms, alpha))
+    return out

@@ -34,7 +34,7 @@ __all__ = [
     "FftPrecomputation", "fft_precompute", "fft", "fft_with_precomputation", "fft_with_precomputation_power_of_2",
     "ifft_with_precomputation_power_of_2", "fft_batch", "coset_lde", "coset_ifft", "divide_by_z_h",
     "field_op", "field_to_bytes", "field_from_bytes", "batch_multiplicative_inverse", "batch_to_affine", "affine_summation_best", "affine_multisummation_best", "curve_mul", "points_generate", "kernel_launch_count",
-    "polynomial_mul", "eval_domain", "from_evaluations", "permutation_polynomial",
+    "polynomial_mul", "eval_domain", "from_evaluations", "permutation_polynomial", "vanishing_points", "vanishing_poly", "fft_subgroup",
     "HaloIpaRounds", "blake_hash_usize_to_curve", "blake_hash_base_field_to_curve", "points_to_bytes", "points_from_bytes",
 ]
 
@@ -126,6 +126,10 @@ def lib():
     L.plk_coset_ifft.argtypes = [vp, u64p, u64p, u64p]
     L.plk_divide_by_z_h.argtypes = [vp, u64p, sz, sz, u64p]
     L.plk_fft_dev.argtypes = [vp, vp, sz, sz, C.c_uint, vp, vp]
+    L.plk_vanishing_points.argtypes = [C.c_int, sz] + [u64p] * 12
+    L.plk_vanishing_points_dev.argtypes = [C.c_int, sz] + [vp] * 8
+    L.plk_vanishing_poly.argtypes = [vp, sz] + [u64p] * 11
+    L.plk_fft_subgroup.argtypes = [vp, u64p]
     L.plk_permutation_polynomial.argtypes = [C.c_int, sz, C.c_uint, u64p, u64p, sz, u64p, sz, sz, u64p, u64p, u64p, u64p]
     L.plk_poly_mul.argtypes = [C.c_int, u64p, sz, u64p, sz, u64p, sz, C.POINTER(sz)]
     L.plk_fft_dist_phase_a.argtypes = [vp, vp, vp, sz, sz, C.c_uint, C.c_uint, vp, vp, vp]
@@ -709,6 +713,49 @@ def polynomial_mul(field: int, a, b) -> np.ndarray:
     n = C.c_size_t()
     _check(lib().plk_poly_mul(field, _p64(a), a.shape[0], _p64(b), b.shape[0], _p64(out), cap, C.byref(n)))
     return out[:n.value].copy()
+
+
+def fft_subgroup(precomputation: "FftPrecomputation") -> np.ndarray:
+    """The plan's evaluation domain w^k, k < size, natural order (Circuit::subgroup_n / subgroup_8n, src/plonk.rs:47-51)."""
+    L = FIELD_LIMBS[precomputation.field]
+    out = np.zeros((precomputation.size(), L), dtype=np.uint64)
+    _check(lib().plk_fft_subgroup(precomputation.handle, _p64(out)))
+    return out
+
+
+def _vanishing_args(field, degree, wires_8n, constants_8n, sigma_8n, k_is, alpha, beta, gamma, inner_zeta, inner_a):
+    L = FIELD_LIMBS[field]
+    m = 8 * degree
+    w = _u64(wires_8n).reshape(9, m, L)
+    c = _u64(constants_8n).reshape(6, m, L)
+    s = _u64(sigma_8n).reshape(6, m, L)
+    small = [_u64(v).reshape(-1, L) for v in (k_is, alpha, beta, gamma, inner_zeta, inner_a)]
+    assert small[0].shape[0] == 6
+    return w, c, s, small
+
+
+def vanishing_points(field: int, degree: int, wires_8n, constants_8n, sigma_8n, z_8n, subgroup_8n, k_is, alpha, beta, gamma, inner_zeta,
+                     inner_a) -> np.ndarray:
+    """The par_iter body of Circuit::vanishing_poly (src/plonk.rs:393-452) over all 8n points: (8n, L) values."""
+    L = FIELD_LIMBS[field]
+    w, c, s, small = _vanishing_args(field, degree, wires_8n, constants_8n, sigma_8n, k_is, alpha, beta, gamma, inner_zeta, inner_a)
+    z = _u64(z_8n).reshape(8 * degree, L)
+    x = _u64(subgroup_8n).reshape(8 * degree, L)
+    out = np.zeros((8 * degree, L), dtype=np.uint64)
+    _check(lib().plk_vanishing_points(field, degree, _p64(w), _p64(c), _p64(s), _p64(z), _p64(x), *[_p64(v) for v in small], _p64(out)))
+    return out
+
+
+def vanishing_poly(fft_precomputation_8n: "FftPrecomputation", degree: int, wires_8n, constants_8n, sigma_8n, plonk_z_coeffs, k_is, alpha, beta,
+                   gamma, inner_zeta, inner_a) -> np.ndarray:
+    """Circuit::vanishing_poly (src/plonk.rs:375-456): the 8n coefficients of the vanishing polynomial."""
+    field = fft_precomputation_8n.field
+    L = FIELD_LIMBS[field]
+    w, c, s, small = _vanishing_args(field, degree, wires_8n, constants_8n, sigma_8n, k_is, alpha, beta, gamma, inner_zeta, inner_a)
+    zc = _u64(plonk_z_coeffs).reshape(degree, L)
+    out = np.zeros((8 * degree, L), dtype=np.uint64)
+    _check(lib().plk_vanishing_poly(fft_precomputation_8n.handle, degree, _p64(w), _p64(c), _p64(s), _p64(zc), *[_p64(v) for v in small], _p64(out)))
+    return out
 
 
 def permutation_polynomial(field: int, subgroup, wire_values, sigma_values, k_is, beta, gamma, num_routed: int = 6,

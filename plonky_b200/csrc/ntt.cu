@@ -1,4 +1,5 @@
 // C ABI of the NTT (include/plonky_b200.h); kernels live in ntt_kernels.cuh, one translation unit per field.
+#include <string.h>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -55,6 +56,24 @@ void check_plan(const plk_fft_plan* p) {
   if (!p) fail(PLK_EINVAL, "NULL plan");
 }
 
+// w^k for k < n on the device (cyclic_subgroup_known_order, src/field/field.rs:292-300), cached in the plan
+const void* plan_subgroup(plk_fft_plan* pl, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(pl->mu);
+  if (!pl->subgroup.p) {
+    const size_t eb = pl->elem_bytes;
+    DevBuf e1(pl->n * eb, st);
+    PLK_CUDA(cudaMemsetAsync(e1.p, 0, pl->n * eb, st));
+    // ONE in Montgomery form = 2^0 of the plan's table of inverse powers of two
+    if (pl->n > 1) PLK_CUDA(cudaMemcpyAsync((char*)e1.p + eb, pl->pow2_inv.p, eb, cudaMemcpyDeviceToDevice, st));
+    else PLK_CUDA(cudaMemcpyAsync(e1.p, pl->pow2_inv.p, eb, cudaMemcpyDeviceToDevice, st));
+    pl->subgroup.alloc(pl->n * eb);
+    FusedOps ops;
+    ops_for(pl->field)->run(pl, e1.p, pl->n, pl->n, pl->subgroup.p, 1, false, &ops, st);
+    PLK_CUDA(cudaStreamSynchronize(st));
+  }
+  return pl->subgroup.p;
+}
+
 }  // namespace
 
 extern "C" {
@@ -80,6 +99,58 @@ int plk_fft_precompute(int field, size_t degree, plk_fft_plan** out) {
       throw;
     }
     *out = pl;
+  });
+}
+
+// Circuit::vanishing_poly (src/plonk.rs:375-456) end to end on the device: pad_to_8n + FFT of the Z coefficients, the
+// pointwise evaluation (vanishing.cu), Polynomial::from_evaluations (the 8n inverse transform).
+int plk_vanishing_poly(const plk_fft_plan* pc, size_t degree, const uint64_t* wires_8n, const uint64_t* constants_8n, const uint64_t* sigma_8n,
+                       const uint64_t* plonk_z_coeffs, const uint64_t* k_is, const uint64_t* alpha, const uint64_t* beta, const uint64_t* gamma,
+                       const uint64_t* inner_zeta, const uint64_t* inner_a, uint64_t* out_coeffs_8n) {
+  return guarded([&] {
+    check_plan(pc);
+    auto* pl = const_cast<plk_fft_plan*>(pc);
+    if (!is_pow2(degree)) fail(PLK_ENOTPOW2, "Not a power of two");
+    if (pl->n != 8 * degree) fail(PLK_ESIZE, "the precomputation must have size 8 * degree (fft_precomputation_8n)");
+    if (pl->elem_bytes != 32) fail(PLK_EINVAL, "vanishing_poly: unsupported field id (4-limb scalar fields only)");
+    if (!wires_8n || !constants_8n || !sigma_8n || !plonk_z_coeffs || !k_is || !alpha || !beta || !gamma || !inner_zeta || !inner_a || !out_coeffs_8n)
+      fail(PLK_EINVAL, "NULL buffer");
+    cudaStream_t st = thread_stream();
+    const size_t m = pl->n, eb = 32;
+    DevBuf d_w(9 * m * eb, st), d_c(6 * m * eb, st), d_s(6 * m * eb, st), d_zc(degree * eb, st), d_z8(m * eb, st), d_p(11 * eb, st), d_pts(m * eb, st),
+        d_out(m * eb, st);
+    PLK_CUDA(cudaMemcpyAsync(d_w.p, wires_8n, 9 * m * eb, cudaMemcpyHostToDevice, st));
+    PLK_CUDA(cudaMemcpyAsync(d_c.p, constants_8n, 6 * m * eb, cudaMemcpyHostToDevice, st));
+    PLK_CUDA(cudaMemcpyAsync(d_s.p, sigma_8n, 6 * m * eb, cudaMemcpyHostToDevice, st));
+    PLK_CUDA(cudaMemcpyAsync(d_zc.p, plonk_z_coeffs, degree * eb, cudaMemcpyHostToDevice, st));
+    uint64_t params[11 * 4];
+    memcpy(params, k_is, 6 * eb);
+    memcpy(params + 24, alpha, eb);
+    memcpy(params + 28, beta, eb);
+    memcpy(params + 32, gamma, eb);
+    memcpy(params + 36, inner_zeta, eb);
+    memcpy(params + 40, inner_a, eb);
+    PLK_CUDA(cudaMemcpyAsync(d_p.p, params, sizeof(params), cudaMemcpyHostToDevice, st));
+    const void* sub = plan_subgroup(pl, st);
+    FusedOps ops;
+    ops_for(pl->field)->run(pl, d_zc.p, degree, degree, d_z8.p, 1, false, &ops, st);                 // plonk.rs:388-391
+    const int rc = plk_vanishing_points_dev(pl->field, degree, d_w.p, d_c.p, d_s.p, d_z8.p, sub, d_p.p, d_pts.p, st);
+    if (rc != PLK_OK) fail(rc, plk_last_error_message());
+    ops_for(pl->field)->run(pl, d_pts.p, m, m, d_out.p, 1, true, &ops, st);                          // plonk.rs:455
+    PLK_CUDA(cudaMemcpyAsync(out_coeffs_8n, d_out.p, m * eb, cudaMemcpyDeviceToHost, st));
+    PLK_CUDA(cudaStreamSynchronize(st));
+  });
+}
+// the plan's subgroup w^k, k < size (self.subgroup_n / subgroup_8n of the reference's Circuit, plonk.rs:47-51)
+int plk_fft_subgroup(const plk_fft_plan* pc, uint64_t* out) {
+  return guarded([&] {
+    check_plan(pc);
+    if (!out) fail(PLK_EINVAL, "NULL buffer");
+    auto* pl = const_cast<plk_fft_plan*>(pc);
+    cudaStream_t st = thread_stream();
+    const void* sub = plan_subgroup(pl, st);
+    PLK_CUDA(cudaMemcpyAsync(out, sub, pl->n * pl->elem_bytes, cudaMemcpyDeviceToHost, st));
+    PLK_CUDA(cudaStreamSynchronize(st));
   });
 }
 

@@ -36,6 +36,7 @@ struct plk_fft_plan {
   plk::DevBuf direct[3][plk::kMaxDigits];
   plk::DevBuf n_inv;              // one element: n^-1
   plk::DevBuf pow2_inv;           // 2^-k, k <= TWO_ADICITY
+  plk::DevBuf subgroup;           // w^k, k < n, natural order (built on first use: the transform of the unit vector e_1)
   std::mutex mu;
   std::map<std::vector<uint32_t>, CosetTables*> cosets;   // keyed by the shift's limbs
   std::map<size_t, plk::DevBuf*> zh_tables;                     // keyed by n_gates
