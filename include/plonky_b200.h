@@ -153,6 +153,12 @@ typedef struct plk_fft_plan plk_fft_plan;       /* = FftPrecomputation<F> (fft.r
 /* fft_precompute(degree) (fft.rs:47-59): the plan size is 2^log2_ceil(degree). */
 int plk_fft_precompute(int field, size_t degree, plk_fft_plan** out);
 size_t plk_fft_size(const plk_fft_plan* p);     /* FftPrecomputation::size (fft.rs:36-40) */
+/* Memory / speed knob.  The passes after the first multiply every element by an inter-pass twiddle w_N^e.  By default a
+ * pass whose twiddle table has at most 2^24 entries reads it from a full table (built lazily, per direction: up to
+ * N * 32 bytes for the last pass of a size-N transform); with log2_entries = 0 every twiddle is formed on the fly from two
+ * tables of sqrt(N) entries and one extra product (no N-entry table ever exists, ~10 % slower at 2^24).  Applies to
+ * transforms issued after the call; tables already built are kept. */
+int plk_fft_set_direct_log(plk_fft_plan* p, int log2_entries);
 void plk_fft_free(plk_fft_plan* p);
 
 /* fft_with_precomputation_power_of_2(coefficients, &pre) (fft.rs:103-156): natural order in,
@@ -250,6 +256,24 @@ int plk_fft_dist_phase_a(const plk_fft_plan* plan_m, const plk_fft_plan* plan_n,
                          void* d_send, void* stream);
 int plk_fft_dist_phase_b(const plk_fft_plan* plan_n, void* d_recv, unsigned log_r1, unsigned log_cols,
                          unsigned flags, void* stream);
+/* Phase A with the exchange fused into the kernel (NVLink peer stores instead of a collective): the last pass writes
+ * each value directly into the receive buffer of the GPU that owns its column block.  peer_recv: `world` device
+ * pointers (host array), peer_recv[d] = rank d's receive buffer ([R1][M / world] elements) as mapped into THIS process
+ * (plk_ipc_open; the rank's own buffer for d == rank).  world <= 8.  The caller must order "every rank finished phase A"
+ * before phase B reads (e.g. one 1-element all-reduce on the stream) and use two receive buffers alternately so that a
+ * fast rank's next transform cannot overwrite a buffer a slow rank is still reading. */
+int plk_fft_dist_phase_a_p2p(const plk_fft_plan* plan_m, const plk_fft_plan* plan_n, const void* d_in,
+                             size_t rows, size_t row_base, unsigned world, unsigned flags, void* d_work,
+                             void* const* peer_recv, void* stream);
+/* cudaMalloc'ed buffers that the other processes of the node can map over NVLink (cudaIpcGetMemHandle /
+ * cudaIpcOpenMemHandle): plk_ipc_alloc returns the buffer and its 64-byte handle (exchange it with the peers by any
+ * means, e.g. torch.distributed.all_gather_object), plk_ipc_open maps a peer's handle, plk_ipc_close unmaps it,
+ * plk_ipc_free releases an owned buffer.  plk_copy_dev: asynchronous device-to-device copy on `stream`. */
+int plk_ipc_alloc(size_t bytes, void** d_ptr, uint8_t handle[64]);
+int plk_ipc_open(const uint8_t handle[64], void** d_ptr);
+int plk_ipc_close(void* d_ptr);
+int plk_ipc_free(void* d_ptr);
+int plk_copy_dev(void* d_dst, const void* d_src, size_t bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Helpers on the same arithmetic (used by the parity tests and by callers that stay on device)

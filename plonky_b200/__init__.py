@@ -114,6 +114,7 @@ def lib():
     L.plk_msm_partial_limbs.argtypes = [C.c_int]
     L.plk_msm_partial_limbs.restype = sz
     L.plk_fft_precompute.argtypes = [C.c_int, sz, C.POINTER(vp)]
+    L.plk_fft_set_direct_log.argtypes = [vp, C.c_int]
     L.plk_fft_size.argtypes = [vp]
     L.plk_fft_size.restype = sz
     L.plk_fft_free.argtypes = [vp]
@@ -134,6 +135,12 @@ def lib():
     L.plk_poly_mul.argtypes = [C.c_int, u64p, sz, u64p, sz, u64p, sz, C.POINTER(sz)]
     L.plk_fft_dist_phase_a.argtypes = [vp, vp, vp, sz, sz, C.c_uint, C.c_uint, vp, vp, vp]
     L.plk_fft_dist_phase_b.argtypes = [vp, vp, C.c_uint, C.c_uint, C.c_uint, vp]
+    L.plk_fft_dist_phase_a_p2p.argtypes = [vp, vp, vp, sz, sz, C.c_uint, C.c_uint, vp, C.POINTER(vp), vp]
+    L.plk_ipc_alloc.argtypes = [sz, C.POINTER(vp), u8p]
+    L.plk_ipc_open.argtypes = [u8p, C.POINTER(vp)]
+    L.plk_ipc_close.argtypes = [vp]
+    L.plk_ipc_free.argtypes = [vp]
+    L.plk_copy_dev.argtypes = [vp, vp, sz, vp]
     L.plk_field_op.argtypes = [C.c_int, C.c_int, u64p, u64p, u64p, sz]
     L.plk_batch_inverse.argtypes = [C.c_int, u64p, u64p, sz]
     L.plk_field_to_bytes.argtypes = [C.c_int, u64p, sz, u8p]
@@ -373,6 +380,10 @@ class FftPrecomputation:
 
     def size(self) -> int:
         return int(lib().plk_fft_size(self.handle))
+
+    def set_direct_log(self, log2_entries: int):
+        """0: inter-pass twiddles always on the fly (no N-entry table); default 24 (see plk_fft_set_direct_log)."""
+        _check(lib().plk_fft_set_direct_log(self.handle, log2_entries))
 
     def close(self):
         if self.handle:

@@ -38,16 +38,26 @@ static void ensure_ctx() {
   PLK_CUDA(cudaStreamCreateWithFlags(&t_ctx.stream, cudaStreamNonBlocking));
   t_ctx.device = dev;
 }
-void ensure_async_pool() {
-  static thread_local int done_for = -1;
+// The library's OWN stream-ordered memory pool, one per device (never the device's default pool, which other users of the
+// process -- e.g. PyTorch with the cudaMallocAsync backend -- share): freed temporaries stay cached up to 1 GiB per device.
+static std::mutex g_pool_mu;
+static cudaMemPool_t g_pools[64] = {};
+cudaMemPool_t async_pool() {
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || done_for == dev) return;
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-    unsigned long long keep = ~0ull;            // never hand cached blocks back to the driver
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  PLK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) fail(PLK_EINVAL, "device index out of range");
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (!g_pools[dev]) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    PLK_CUDA(cudaMemPoolCreate(&g_pools[dev], &props));
+    unsigned long long keep = 1ull << 30;
+    cudaMemPoolSetAttribute(g_pools[dev], cudaMemPoolAttrReleaseThreshold, &keep);
   }
-  done_for = dev;
+  return g_pools[dev];
 }
 cudaStream_t thread_stream() {
   ensure_ctx();

@@ -73,9 +73,9 @@ cudaStream_t thread_stream();
 void* thread_scratch(int slot, size_t bytes);
 
 // Device buffer.  Long-lived buffers (tables, plans) use cudaMalloc; temporaries of one call use the
-// stream-ordered allocator (cudaMallocAsync / cudaFreeAsync on the call's stream, pool never trimmed), which
+// stream-ordered allocator (cudaMallocFromPoolAsync / cudaFreeAsync on the call's stream, a private pool per device), which
 // costs microseconds instead of the ~0.1-0.5 ms and implicit device synchronisation of cudaMalloc / cudaFree.
-void ensure_async_pool();
+cudaMemPool_t async_pool();      // the library's private pool on the current device
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
@@ -96,7 +96,7 @@ struct DevBuf {
   void alloc(size_t b) {
     release();
     if (b == 0) b = 16;
-    if (async) { ensure_async_pool(); PLK_CUDA(cudaMallocAsync(&p, b, astream)); }
+    if (async) PLK_CUDA(cudaMallocFromPoolAsync(&p, b, async_pool(), astream));
     else PLK_CUDA(cudaMalloc(&p, b));
     bytes = b;
   }
@@ -119,7 +119,7 @@ struct PhaseTimer {
   int n = 0;        // events recorded in the last call
   bool created = false;
   void begin(cudaStream_t st) {
-    if (!g_profiling.load(std::memory_order_relaxed)) { n = 0; return; }
+    if (!g_profiling.load(std::memory_order_relaxed)) return;          // not profiling: the timer is never written (shared plans stay read-only)
     if (!created) { for (auto& e : ev) PLK_CUDA(cudaEventCreate(&e)); created = true; }
     n = 0;
     mark(st);

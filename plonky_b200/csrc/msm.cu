@@ -125,9 +125,16 @@ void run_one(plk_msm_table* t, const void* d_scalars, void* d_out_xyz, void* d_o
 }
 // k executes on device buffers, forked round-robin onto the table's side streams and joined back on `st`: the
 // low-occupancy reduction tails of one MSM overlap with the sort / accumulation of the next ones.
-void run_batch(plk_msm_table* t, const char* d_scalars, size_t k, char* d_out_xyz, char* d_out_zero, cudaStream_t st) {
+// h_scalars (optional): host copy of the k scalar vectors; vector j is then copied to d_scalars + j * sbytes on the side
+// stream that executes it, so the copy of one vector overlaps the accumulation of the previous ones.
+void run_batch(plk_msm_table* t, const char* d_scalars, size_t k, char* d_out_xyz, char* d_out_zero, cudaStream_t st,
+               const char* h_scalars = nullptr) {
   const size_t L = curve_base_limbs64(t->curve), sbytes = t->n * 32;
-  if (k == 1) { run_one(t, d_scalars, d_out_xyz, d_out_zero, nullptr, st); return; }
+  if (k == 1) {
+    if (h_scalars && sbytes) PLK_CUDA(cudaMemcpyAsync(const_cast<char*>(d_scalars), h_scalars, sbytes, cudaMemcpyHostToDevice, st));
+    run_one(t, d_scalars, d_out_xyz, d_out_zero, nullptr, st);
+    return;
+  }
   std::lock_guard<std::mutex> batch_lock(t->batch_mu);
   {
     std::lock_guard<std::mutex> lk(t->mu);
@@ -146,8 +153,11 @@ void run_batch(plk_msm_table* t, const char* d_scalars, size_t k, char* d_out_xy
   const int S = t->side_streams;
   PLK_CUDA(cudaEventRecord(t->fork_ev, st));
   for (int i = 0; i < S && (size_t)i < k; ++i) PLK_CUDA(cudaStreamWaitEvent(t->side[i], t->fork_ev, 0));
-  for (size_t j = 0; j < k; ++j)
+  for (size_t j = 0; j < k; ++j) {
+    if (h_scalars && sbytes)
+      PLK_CUDA(cudaMemcpyAsync(const_cast<char*>(d_scalars) + j * sbytes, h_scalars + j * sbytes, sbytes, cudaMemcpyHostToDevice, t->side[j % S]));
     run_one(t, d_scalars + j * sbytes, d_out_xyz + j * 3 * L * 8, d_out_zero + j, nullptr, t->side[j % S]);
+  }
   for (int i = 0; i < S && (size_t)i < k; ++i) {
     PLK_CUDA(cudaEventRecord(t->join_ev[i], t->side[i]));
     PLK_CUDA(cudaStreamWaitEvent(st, t->join_ev[i], 0));
@@ -233,8 +243,7 @@ void execute_host(plk_msm_table* t, const uint64_t* scalars, size_t n, size_t k,
   const size_t sbytes = n * 32;
   char* d_s = reinterpret_cast<char*>(thread_scratch(0, sbytes * k + 16));
   char* d_o = reinterpret_cast<char*>(thread_scratch(1, k * (3 * L * 8 + 8)));
-  if (n) PLK_CUDA(cudaMemcpyAsync(d_s, scalars, sbytes * k, cudaMemcpyHostToDevice, st));
-  run_batch(t, d_s, k, d_o, d_o + k * 3 * L * 8, st);
+  run_batch(t, d_s, k, d_o, d_o + k * 3 * L * 8, st, reinterpret_cast<const char*>(scalars));
   PLK_CUDA(cudaMemcpyAsync(out_xyz, d_o, k * 3 * L * 8, cudaMemcpyDeviceToHost, st));
   PLK_CUDA(cudaMemcpyAsync(out_zero, d_o + k * 3 * L * 8, k, cudaMemcpyDeviceToHost, st));
   PLK_CUDA(cudaStreamSynchronize(st));
@@ -356,6 +365,7 @@ int plk_msm_last_phase_ms(const plk_msm_table* tc, float* out_ms, int cap) {
   int rc = guarded([&] {
     auto* t = const_cast<plk_msm_table*>(tc);
     if (!t || !out_ms) fail(PLK_EINVAL, "bad arguments");
+    std::lock_guard<std::mutex> lk(t->mu);
     if (!t->last) fail(PLK_EINVAL, "no execute has run against this table");
     n = t->last->timer.read(out_ms, cap);
   });
@@ -387,9 +397,8 @@ int plk_commit_batch(const plk_msm_table* tc, const uint64_t* scalars, size_t n,
     // msm results (k * 3L u64 + k flags), blinding factors, outputs (k * 2L u64 + k flags)
     const size_t o_msm = 0, o_mz = k * 3 * L * 8, o_bl = o_mz + ((k + 15) / 16) * 16, o_out = o_bl + k * 32, o_oz = o_out + k * 2 * L * 8;
     char* d_o = reinterpret_cast<char*>(thread_scratch(1, o_oz + k + 16));
-    if (n) PLK_CUDA(cudaMemcpyAsync(d_s, scalars, sbytes * k, cudaMemcpyHostToDevice, st));
     if (blinding) PLK_CUDA(cudaMemcpyAsync(d_o + o_bl, blinding, k * 32, cudaMemcpyHostToDevice, st));
-    run_batch(t, d_s, k, d_o + o_msm, d_o + o_mz, st);
+    run_batch(t, d_s, k, d_o + o_msm, d_o + o_mz, st, reinterpret_cast<const char*>(scalars));
     ops_for(t->curve)->commit_blind(d_o + o_msm, reinterpret_cast<unsigned char*>(d_o + o_mz), blinding ? d_o + o_bl : nullptr, h_xy, h_zero != 0, k,
                                     d_o + o_out, reinterpret_cast<unsigned char*>(d_o + o_oz), st);
     PLK_CUDA(cudaMemcpyAsync(out_xy, d_o + o_out, k * 2 * L * 8, cudaMemcpyDeviceToHost, st));

@@ -465,17 +465,21 @@ __global__ void __launch_bounds__(128) msm_table_kernel(const void* __restrict__
   for (int j = 1; j < nwin; ++j) {
     for (int k = 0; k < c; ++k) q = XYZZ<C>::dbl(q);
     const size_t slot = (size_t)j * n + i;
-    store_fp<F>(table, 2 * slot, q.x);
-    store_fp<F>(table, 2 * slot + 1, q.y);
-    store_fp<F>(scratch, 3 * slot, q.zz);
+    // A power can be the identity when the generator has 2-power order (BLS12-377 G1 has an even cofactor: e.g. (-1, 0)
+    // on y^2 = x^3 + 1): it and every later power are stored as the identity and stay out of the batch product.
+    const bool dead = q.is_identity();
+    store_fp<F>(table, 2 * slot, dead ? F::zero() : q.x);
+    store_fp<F>(table, 2 * slot + 1, dead ? F::zero() : q.y);
+    store_fp<F>(scratch, 3 * slot, q.zz);                 // zz == 0 marks an identity power for the backward sweep
     store_fp<F>(scratch, 3 * slot + 1, q.zzz);
-    store_fp<F>(scratch, 3 * slot + 2, prod);          // product of the ZZ*ZZZ of the powers before this one
-    prod = F::mul(prod, F::mul(q.zz, q.zzz));           // never zero: the group has odd order, no power is the identity
+    store_fp<F>(scratch, 3 * slot + 2, prod);             // product of the ZZ*ZZZ of the live powers before this one
+    if (!dead) prod = F::mul(prod, F::mul(q.zz, q.zzz));
   }
   F inv = F::inverse(prod);
   for (int j = nwin - 1; j >= 1; --j) {
     const size_t slot = (size_t)j * n + i;
     const F zz = load_fp<F>(scratch, 3 * slot), zzz = load_fp<F>(scratch, 3 * slot + 1), before = load_fp<F>(scratch, 3 * slot + 2);
+    if (zz.is_zero()) continue;                           // identity power: (0, 0) is already in the table
     const F inv_j = F::mul(inv, before);                // 1 / (zz * zzz)
     inv = F::mul(inv, F::mul(zz, zzz));
     const F x = F::mul(load_fp<F>(table, 2 * slot), F::mul(inv_j, zzz));      // X / ZZ

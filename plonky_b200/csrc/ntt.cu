@@ -1,6 +1,8 @@
 // C ABI of the NTT (include/plonky_b200.h); kernels live in ntt_kernels.cuh, one translation unit per field.
+#include <stdlib.h>
 #include <string.h>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <tuple>
 #include "ntt_plan.h"
@@ -58,7 +60,7 @@ void check_plan(const plk_fft_plan* p) {
 
 // w^k for k < n on the device (cyclic_subgroup_known_order, src/field/field.rs:292-300), cached in the plan
 const void* plan_subgroup(plk_fft_plan* pl, cudaStream_t st) {
-  std::lock_guard<std::mutex> lk(pl->mu);
+  std::lock_guard<std::mutex> lk(pl->sub_mu);        // not pl->mu: the transform below takes that one (lazy twiddle tables)
   if (!pl->subgroup.p) {
     const size_t eb = pl->elem_bytes;
     DevBuf e1(pl->n * eb, st);
@@ -92,6 +94,8 @@ int plk_fft_precompute(int field, size_t degree, plk_fft_plan** out) {
     pl->log_n = L;
     pl->n = (size_t)1 << L;
     cudaGetDevice(&pl->device);
+    if (const char* e = getenv("PLK_NTT_DIRECT_LOG")) pl->direct_log = atoi(e);
+    if (getenv("PLK_NTT_NO_DIRECT")) pl->direct_log = 0;
     try {
       ops_for(field)->plan_build(pl);
     } catch (...) {
@@ -154,6 +158,14 @@ int plk_fft_subgroup(const plk_fft_plan* pc, uint64_t* out) {
   });
 }
 
+int plk_fft_set_direct_log(plk_fft_plan* p, int log2_entries) {
+  return guarded([&] {
+    check_plan(p);
+    if (log2_entries < 0 || log2_entries > 30) fail(PLK_EINVAL, "direct table cap out of range");
+    std::lock_guard<std::mutex> lk(p->mu);
+    p->direct_log = log2_entries;
+  });
+}
 size_t plk_fft_size(const plk_fft_plan* p) { return p ? p->n : 0; }
 int plk_fft_num_passes(const plk_fft_plan* p) { return p ? p->m : 0; }
 int plk_fft_last_pass_ms(const plk_fft_plan* pc, float* out_ms, int cap) {
@@ -161,6 +173,7 @@ int plk_fft_last_pass_ms(const plk_fft_plan* pc, float* out_ms, int cap) {
   int rc = guarded([&] {
     auto* p = const_cast<plk_fft_plan*>(pc);
     if (!p || !out_ms) fail(PLK_EINVAL, "bad arguments");
+    std::lock_guard<std::mutex> lk(p->timer_mu);
     n = p->timer.read(out_ms, cap);
   });
   return rc == PLK_OK ? n : -rc;
@@ -293,8 +306,11 @@ int plk_poly_mul(int field, const uint64_t* a, size_t na, const uint64_t* b, siz
     static std::map<std::tuple<int, int, int>, plk_fft_plan*> cache;
     int dev = 0;
     PLK_CUDA(cudaGetDevice(&dev));
+    // plans up to 2^20 are cached for the life of the process (a few MiB each: direct twiddle tables are built lazily and
+    // only in the directions used); larger products build their plan for this call and free it afterwards
     plk_fft_plan* pl = nullptr;
-    {
+    std::unique_ptr<plk_fft_plan> transient;
+    if (lg <= 20) {
       std::lock_guard<std::mutex> lk(mu);
       auto key = std::make_tuple(field, lg, dev);
       auto it = cache.find(key);
@@ -305,6 +321,12 @@ int plk_poly_mul(int field, const uint64_t* a, size_t na, const uint64_t* b, siz
         it = cache.emplace(key, fresh).first;
       }
       pl = it->second;
+    } else {
+      plk_fft_plan* fresh = nullptr;
+      const int rc = plk_fft_precompute(field, n, &fresh);
+      if (rc != PLK_OK) fail(rc, plk_last_error_message());
+      transient.reset(fresh);
+      pl = fresh;
     }
     cudaStream_t st = thread_stream();
     const size_t eb = pl->elem_bytes;
@@ -367,6 +389,65 @@ int plk_fft_dist_phase_a(const plk_fft_plan* plan_m, const plk_fft_plan* plan_n,
     ops.remap_cl_log = plan_m->log_n - log2_floor(world);
     ops.remap_rows = rows;
     ops_for(plan_m->field)->run(plan_m, d_in, plan_m->n, plan_m->n, d_work, rows, inverse, &ops, reinterpret_cast<cudaStream_t>(stream));
+  });
+}
+// Phase A with the exchange folded into the kernel: the last pass stores every value straight into the receive buffer
+// of the GPU that owns its column block (peer_recv[d] = that GPU's buffer, mapped here with plk_ipc_open; this rank's own
+// buffer for d == rank), so no send buffer and no all-to-all exist.  The caller orders "all peers finished phase A" before
+// phase B (one tiny all-reduce on the stream) and alternates between two receive buffers per transform.
+int plk_fft_dist_phase_a_p2p(const plk_fft_plan* plan_m, const plk_fft_plan* plan_n, const void* d_in, size_t rows, size_t row_base,
+                             unsigned world, unsigned flags, void* d_work, void* const* peer_recv, void* stream) {
+  return guarded([&] {
+    check_plan(plan_m);
+    check_plan(plan_n);
+    if (!d_in || !d_work || !peer_recv || rows == 0 || world == 0) fail(PLK_EINVAL, "bad arguments");
+    if (plan_m->field != plan_n->field || plan_m->log_n > plan_n->log_n) fail(PLK_EINVAL, "plans do not match");
+    if (!is_pow2(world) || world > plan_m->n || world > (unsigned)kMaxPeers) fail(PLK_EINVAL, "world must be a power of two <= min(M, 8)");
+    if (rows > 65535) fail(PLK_EINVAL, "too many local rows");
+    const bool inverse = (flags & PLK_FFT_INVERSE) != 0;
+    FusedOps ops;
+    ops.post_lo = plan_n->tw_lo[inverse ? 1 : 0].p;
+    ops.post_hi = plan_n->tw_hi[inverse ? 1 : 0].p;
+    ops.post_lo_bits = plan_n->lo_bits;
+    ops.post_rowmul = 1;
+    ops.post_row_base = row_base;
+    ops.remap = 2;
+    ops.remap_cl_log = plan_m->log_n - log2_floor(world);
+    ops.remap_rows = rows;
+    ops.remap_row_base = row_base;
+    for (unsigned d = 0; d < world; ++d) {
+      if (!peer_recv[d]) fail(PLK_EINVAL, "NULL peer buffer");
+      ops.peer[d] = peer_recv[d];
+    }
+    ops_for(plan_m->field)->run(plan_m, d_in, plan_m->n, plan_m->n, d_work, rows, inverse, &ops, reinterpret_cast<cudaStream_t>(stream));
+  });
+}
+// Device buffers that other processes of the node can map (cudaIpc*): the receive buffers of the domain-split transform.
+int plk_ipc_alloc(size_t bytes, void** d_ptr, uint8_t handle[64]) {
+  return guarded([&] {
+    if (!d_ptr || !handle || bytes == 0) fail(PLK_EINVAL, "bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    PLK_CUDA(cudaMalloc(d_ptr, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, *d_ptr);
+    if (e != cudaSuccess) { cudaFree(*d_ptr); *d_ptr = nullptr; throw ::plk::CudaError{e, "cudaIpcGetMemHandle", __FILE__, __LINE__}; }
+    memcpy(handle, &h, 64);
+  });
+}
+int plk_ipc_open(const uint8_t handle[64], void** d_ptr) {
+  return guarded([&] {
+    if (!d_ptr || !handle) fail(PLK_EINVAL, "bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    PLK_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  });
+}
+int plk_ipc_close(void* d_ptr) { return guarded([&] { if (d_ptr) PLK_CUDA(cudaIpcCloseMemHandle(d_ptr)); }); }
+int plk_ipc_free(void* d_ptr) { return guarded([&] { if (d_ptr) PLK_CUDA(cudaFree(d_ptr)); }); }
+int plk_copy_dev(void* d_dst, const void* d_src, size_t bytes, void* stream) {
+  return guarded([&] {
+    if (bytes && (!d_dst || !d_src)) fail(PLK_EINVAL, "NULL buffer");
+    PLK_CUDA(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(stream)));
   });
 }
 int plk_fft_dist_phase_b(const plk_fft_plan* plan_n, void* d_recv, unsigned log_r1, unsigned log_cols, unsigned flags, void* stream) {

@@ -2,6 +2,7 @@
 #pragma once
 #include <stdlib.h>
 #include "ntt_kernels.cuh"
+#include "ntt_tma.cuh"
 
 // defined in api.cu: out[i] = in[i]^-1 elementwise on device
 void plk_launch_field_inverse(int field, const void* d_in, void* d_out, size_t n, cudaStream_t st);
@@ -51,29 +52,33 @@ void plan_build(plk_fft_plan* pl) {
     build_pow_table<P>(wn, pl->lo_bits, (size_t)1 << (L - pl->lo_bits), nullptr, pl->tw_hi[inv], st);
     if (inv) build_pow_table<P>(wn, pl->lo_bits, (size_t)1 << (L - pl->lo_bits), pl->n_inv.p, pl->tw_hi_inv_scaled, st);
   }
-  // direct twiddle tables for the in-place passes with a small N_d (digit d is processed with M_d = 2^(r_{d+1}+..+r_m))
-  {
-    int log_m_acc = pl->dig[pl->m - 1];
-    for (int d = pl->m - 2; d >= 0; --d) {
-      const int r = pl->dig[d], log_nd = r + log_m_acc, sh = L - log_nd;
-      static const int direct_log = getenv("PLK_NTT_DIRECT_LOG") ? atoi(getenv("PLK_NTT_DIRECT_LOG")) : kDirectLog;
-      if (log_nd <= direct_log && !getenv("PLK_NTT_NO_DIRECT")) {
-        const size_t cnt = (size_t)1 << log_nd;
-        const unsigned blocks = (unsigned)((cnt + 127) / 128);
-        for (int v = 0; v < 3; ++v) {
-          if (v == 2 && d != 0) continue;                  // the scaled table only serves the last pass (digit 1) ...
-          if (v == 1 && d == 0) continue;                  // ... which never uses the unscaled inverse one
-          pl->direct[v][d].alloc(cnt * sizeof(F));
-          const int inv = v ? 1 : 0;
-          direct_twiddle_kernel<F><<<blocks, 128, 0, st>>>(pl->tw_lo[inv].p, v == 2 ? pl->tw_hi_inv_scaled.p : pl->tw_hi[inv].p, pl->lo_bits,
-                                                       log_m_acc, r, sh, v == 2 ? 1 : 0, pl->direct[v][d].template as<F>());
-          PLK_LAUNCHED();
-        }
-      }
-      log_m_acc += r;
-    }
-  }
+  // the full inter-pass twiddle tables of the in-place passes (ensure_direct) are built on first use, per direction
   PLK_CUDA(cudaStreamSynchronize(st));
+}
+
+// Full twiddle table w_{N_d}^(j_d k'') of the in-place pass over digit d in direction v (0 forward, 1 inverse, 2 inverse with
+// n^-1 folded in: the last pass), built on first use when N_d <= 2^kDirectLog (plk_fft_set_direct_log / PLK_NTT_DIRECT_LOG lower the cap,
+// 0 or PLK_NTT_NO_DIRECT=1 disable it: the pass then forms each twiddle on the fly from two small tables and one more product).
+// A plan that only ever runs forward never allocates the inverse tables; a plan that only lends its small tables to the
+// domain-split transform allocates none.
+template <class P>
+const void* ensure_direct(const plk_fft_plan* plc, int v, int d, int log_m_acc, cudaStream_t st) {
+  typedef Fp<P> F;
+  plk_fft_plan* pl = const_cast<plk_fft_plan*>(plc);
+  const int r = pl->dig[d], log_nd = r + log_m_acc, sh = pl->log_n - log_nd;
+  if (log_nd > pl->direct_log) return nullptr;
+  std::lock_guard<std::mutex> lk(pl->mu);
+  if (!pl->direct[v][d].p) {
+    const size_t cnt = (size_t)1 << log_nd;
+    pl->direct[v][d].alloc(cnt * sizeof(F));
+    const int inv = v ? 1 : 0;
+    direct_twiddle_kernel<F><<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>(pl->tw_lo[inv].p, v == 2 ? pl->tw_hi_inv_scaled.p : pl->tw_hi[inv].p,
+                                                                            pl->lo_bits, log_m_acc, r, sh, v == 2 ? 1 : 0,
+                                                                            pl->direct[v][d].template as<F>());
+    PLK_LAUNCHED();
+    PLK_CUDA(cudaStreamSynchronize(st));       // other streams may use the table as soon as the lock is released
+  }
+  return pl->direct[v][d].p;
 }
 
 // One transform of k rows: d_in (n_in elements per row, stride in_stride) -> d_out (n per row).
@@ -85,7 +90,8 @@ void run_ntt(const plk_fft_plan* pl, const void* d_in, size_t n_in, size_t in_st
   const int L = pl->log_n;
   const int m = pl->m;
   const int inv = inverse ? 1 : 0;
-  static bool attr_set[8] = {false};
+  static std::mutex attr_mu;
+  static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   const size_t wsub_bytes = sizeof(F) << (kSubLog - 1);
@@ -95,13 +101,19 @@ void run_ntt(const plk_fft_plan* pl, const void* d_in, size_t n_in, size_t in_st
   static const int nthreads = getenv("PLK_NTT_THREADS") ? atoi(getenv("PLK_NTT_THREADS")) : kNttThreads;
   // radix-4 register rounds at 3 CTAs / SM measured 6 % faster than radix-8 at 2 CTAs / SM (PLK_NTT_RADIX4=0 selects the latter)
   static const int radix4 = getenv("PLK_NTT_RADIX4") ? atoi(getenv("PLK_NTT_RADIX4")) : 1;
-  if (!attr_set[dev & 7]) {
-    PLK_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<F, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-    PLK_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<F, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-    attr_set[dev & 7] = true;
+  {
+    std::lock_guard<std::mutex> lk(attr_mu);                   // the opt-in to > 48 KiB of dynamic shared memory is per device
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+      PLK_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<F, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+      PLK_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<F, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
   }
   int log_m_acc = 0;   // log2 of M_d for the pass being issued
+  // per-pass CUDA events only when profiling is on, and then under the plan's timer lock (concurrent callers share the plan)
   PhaseTimer& timer = const_cast<plk_fft_plan*>(pl)->timer;
+  std::unique_lock<std::mutex> timer_lock;
+  if (g_profiling.load(std::memory_order_relaxed)) timer_lock = std::unique_lock<std::mutex>(const_cast<plk_fft_plan*>(pl)->timer_mu);
   timer.begin(st);
   for (int pass = 0; pass < m; ++pass) {
     const int d = m - 1 - pass;          // digit index (0-based): pass 0 handles r_m
@@ -132,7 +144,7 @@ void run_ntt(const plk_fft_plan* pl, const void* d_in, size_t n_in, size_t in_st
       p.log_t = p.log_m < tile_log ? p.log_m : tile_log;
       if (inverse && p.last) { p.tw_all = 1; p.tw_hi = pl->tw_hi_inv_scaled.p; }
       const int v = (inverse && p.last) ? 2 : inv;
-      if (pl->direct[v][d].p) p.tw_direct = pl->direct[v][d].p;
+      p.tw_direct = ensure_direct<P>(pl, v, d, log_m_acc, st);
     }
     if (p.last) {
       p.post_lo = ops.post_lo;
@@ -144,10 +156,17 @@ void run_ntt(const plk_fft_plan* pl, const void* d_in, size_t n_in, size_t in_st
       p.remap = ops.remap;
       p.remap_cl_log = ops.remap_cl_log;
       p.remap_rows = ops.remap_rows;
+      p.remap_row_base = ops.remap_row_base;
+      for (int i = 0; i < kMaxPeers; ++i) p.peer[i] = ops.peer[i];
       if (ops.final_out) p.out = ops.final_out;
     }
     // the post tables may belong to the (larger) plan of a distributed transform: their own lo_bits
     p.post_lo_bits = (p.last && ops.post_lo_bits >= 0) ? ops.post_lo_bits : p.lo_bits;
+    if (launch_tma_pass<F>(p, pl->n, k, st)) {        // TMA-staged Stockham pass (ntt_tma.cuh) when the geometry qualifies
+      timer.mark(st);
+      log_m_acc += p.r;
+      continue;
+    }
     const size_t tiles = pl->n >> (p.r + p.log_t);
     const size_t smem = (size_t)(F::N / 4) * 16 * ((size_t)1 << (p.r + p.log_t)) + wsub_bytes;
     if (tiles > 0x7fffffffull || k > 65535) fail(PLK_EINVAL, "transform grid too large");
@@ -258,6 +277,7 @@ void do_final_pass(const plk_fft_plan* pl, void* d_buf, int r, int log_cols, boo
   p.lo_bits = pl->lo_bits;
   p.post_lo_bits = pl->lo_bits;
   p.scale = d_scale;
+  if (launch_tma_pass<F>(p, (size_t)1 << (r + log_cols), 1, st)) return;
   const size_t wsub_bytes = sizeof(F) << (kSubLog - 1);
   const size_t smem = (size_t)(F::N / 4) * 16 * ((size_t)1 << (p.r + p.log_t)) + wsub_bytes;
   PLK_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<F, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,

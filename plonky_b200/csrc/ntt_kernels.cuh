@@ -19,8 +19,9 @@
 //   128-bit loads), staged in shared memory as split 16-byte pieces with an XOR swizzle so that
 //   row-wise, column-wise and butterfly accesses are all bank-conflict free.  Butterflies run as
 //   radix-8 / 4 / 2 register rounds (3 / 2 / 1 layers per shared-memory round trip).
-//   Twiddles: sub-transform twiddles from a 128-entry table; inter-pass twiddles w_n^e on the fly
-//   from two small tables (w^lo, w^(hi << lo_bits)) and one multiply -- never an n-entry table.
+//   Twiddles: sub-transform twiddles from a 128-entry table; inter-pass twiddles w_n^e either on the fly from two small
+//   tables (w^lo, w^(hi << lo_bits)) and one multiply, or -- for passes with N_d <= 2^24, built lazily per direction
+//   (ensure_direct, ntt_host.cuh) -- from a full table: one load and one product less per element, N_d * 32 bytes more.
 //   Fused: zero-padding (rows beyond n_in are never read), coset shift c_j g^j on load, n^-1 folded
 //   into the last pass' twiddle table for the inverse, g^-i / pointwise factors on the final store.
 //
@@ -66,6 +67,10 @@ struct NttPassParams {
   int remap;                      // final store goes to the all-to-all send layout [dest][row][k mod 2^remap_cl_log]
   int remap_cl_log;
   unsigned long long remap_rows;
+  // remap == 2: the final store goes STRAIGHT into the receive buffers of the peer GPUs (CUDA IPC mappings over NVLink):
+  // value k of local row `row` lands in peer (k >> remap_cl_log) at [remap_row_base + row][k mod 2^remap_cl_log]
+  void* peer[kMaxPeers];
+  unsigned long long remap_row_base;
 };
 
 // Output position of final value k of batch row `row`: natural (k) or packed for the all-to-all of the
@@ -75,6 +80,15 @@ __device__ __forceinline__ unsigned long long ntt_out_index(const NttPassParams&
   if (!p.remap) return (unsigned long long)row * out_stride + k;
   const unsigned long long dest = k >> p.remap_cl_log, kl = k & ((1ull << p.remap_cl_log) - 1);
   return ((dest * p.remap_rows + row) << p.remap_cl_log) + kl;
+}
+
+// piece 0 of final value k of batch row `row`: local buffer, or a peer's receive buffer (remap == 2)
+__device__ __forceinline__ uint4* ntt_out_ptr(const NttPassParams& p, uint4* out, unsigned long long k, unsigned row, int pieces) {
+  if (p.remap == 2) {
+    const unsigned long long dest = k >> p.remap_cl_log, kl = k & ((1ull << p.remap_cl_log) - 1);
+    return reinterpret_cast<uint4*>(p.peer[dest]) + ((((p.remap_row_base + row) << p.remap_cl_log) + kl) * pieces);
+  }
+  return out + ntt_out_index(p, k, row, p.out_stride) * pieces;
 }
 
 __device__ __forceinline__ unsigned bitrev(unsigned x, int bits) { return bits == 0 ? 0u : (__brev(x) >> (32 - bits)); }
@@ -310,9 +324,9 @@ __global__ void __launch_bounds__(kNttThreads, MAXQ == 3 ? 2 : 3) ntt_pass_kerne
       const int col = e & (T - 1);
       const int row = e >> p.log_t;
       const unsigned long long gidx = g.gbase + col + ((unsigned long long)row << g.rowshift);
-      const unsigned long long oidx = p.last ? ntt_out_index(p, gidx, blockIdx.y, p.out_stride)
-                                             : (unsigned long long)blockIdx.y * p.out_stride + gidx;
-      out[oidx * PIECES + piece] = smem[piece * elems + row * T + (col ^ (row & (T - 1)))];
+      uint4* dst = p.last ? ntt_out_ptr(p, out, gidx, blockIdx.y, PIECES)
+                          : out + ((unsigned long long)blockIdx.y * p.out_stride + gidx) * PIECES;
+      dst[piece] = smem[piece * elems + row * T + (col ^ (row & (T - 1)))];
     }
   } else {
     // column c of the tile becomes a run of R contiguous outputs at rev_digits(jlow) * R
@@ -327,9 +341,9 @@ __global__ void __launch_bounds__(kNttThreads, MAXQ == 3 ? 2 : 3) ntt_pass_kerne
         x >>= p.digs[i];
       }
       const unsigned long long gidx = (pos << p.r) + row;
-      const unsigned long long oidx = p.last ? ntt_out_index(p, gidx, blockIdx.y, p.out_stride)
-                                             : (unsigned long long)blockIdx.y * p.out_stride + gidx;
-      out[oidx * PIECES + piece] = smem[piece * elems + row * T + (col ^ (row & (T - 1)))];
+      uint4* dst = p.last ? ntt_out_ptr(p, out, gidx, blockIdx.y, PIECES)
+                          : out + ((unsigned long long)blockIdx.y * p.out_stride + gidx) * PIECES;
+      dst[piece] = smem[piece * elems + row * T + (col ^ (row & (T - 1)))];
     }
   }
 }

@@ -7,6 +7,7 @@
 
 namespace plk {
 constexpr int kSubLog = 8;          // largest sub-transform: 2^8 rows
+constexpr int kMaxPeers = 8;        // GPUs of one NVSwitch domain the domain-split transform stores into directly
 constexpr int kMaxDigits = 6;       // 6 * 8 = 48 >= largest TWO_ADICITY (47)
 constexpr int kTileColsLog = 3;     // 8 columns per tile
 constexpr int kNttThreads = 256;
@@ -27,6 +28,7 @@ struct plk_fft_plan {
   int m = 0;                 // passes
   int dig[plk::kMaxDigits];       // r_1 .. r_m
   int lo_bits = 0;
+  int direct_log = plk::kDirectLog;   // passes with N_d <= 2^direct_log use a full twiddle table (0: always on the fly)
   size_t elem_bytes = 32;
   plk::DevBuf wsub[2];            // [0] forward, [1] inverse
   plk::DevBuf tw_lo[2], tw_hi[2];
@@ -40,7 +42,9 @@ struct plk_fft_plan {
   std::mutex mu;
   std::map<std::vector<uint32_t>, CosetTables*> cosets;   // keyed by the shift's limbs
   std::map<size_t, plk::DevBuf*> zh_tables;                     // keyed by n_gates
-  plk::PhaseTimer timer;          // one phase per pass of the last transform
+  plk::PhaseTimer timer;          // one phase per pass of the last transform (written only while profiling, under timer_mu)
+  std::mutex timer_mu;
+  std::mutex sub_mu;              // guards the lazy construction of `subgroup`
   ~plk_fft_plan() {
     for (auto& kv : cosets) delete kv.second;
     for (auto& kv : zh_tables) delete kv.second;
@@ -61,8 +65,10 @@ struct FusedOps {
   unsigned long long post_row_base = 0;
   int post_lo_bits = -1;              // lo_bits of the post tables when they belong to another (larger) plan
   void* final_out = nullptr;          // last pass writes here (out of place) instead of d_out
-  int remap = 0, remap_cl_log = 0;
+  int remap = 0, remap_cl_log = 0;    // remap = 2: store into the peers' receive buffers (peer[], remap_row_base)
   unsigned long long remap_rows = 0;
+  void* peer[kMaxPeers] = {};
+  unsigned long long remap_row_base = 0;
 };
 
 

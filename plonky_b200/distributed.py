@@ -156,7 +156,7 @@ class DistributedNtt:
     With world == 1 the input is the R1 x M "decimated" view of x and the output is X in natural order.
     `input_rows(x)` / `gather_natural(out)` convert between these layouts and natural order (tests, G = 1)."""
 
-    def __init__(self, field: int, log_n: int, world: int = None, rank: int = None, group=None, log_r1: int = None):
+    def __init__(self, field: int, log_n: int, world: int = None, rank: int = None, group=None, log_r1: int = None, p2p=None):
         from . import fft_precompute, FIELD_LIMBS as FL
         self.group = group
         self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
@@ -170,13 +170,74 @@ class DistributedNtt:
         self.L = FL[field]
         self.rows = (1 << log_r1) // self.world
         self.cols = (1 << self.log_m) // self.world
-        self.exchange_kind = "NCCL all_to_all_single" if self.world > 1 else "local copy"
         self.plan_m = fft_precompute(field, 1 << self.log_m)
         self.plan_n = fft_precompute(field, 1 << log_n)
         shape_in = (self.rows, 1 << self.log_m, self.L)
         self.work = torch.empty(shape_in, dtype=torch.int64, device="cuda")
         self.send = torch.empty(shape_in, dtype=torch.int64, device="cuda")
         self.recv = torch.empty((1 << log_r1, self.cols, self.L), dtype=torch.int64, device="cuda")
+        self.exchange_kind = "NCCL all_to_all_single" if self.world > 1 else "local copy"
+        self._p2p = None
+        self.copy_out = True       # P2P mode: copy the result from the IPC buffer into self.recv (a torch tensor); the timed
+                                   # loop of bench.py switches it off and reads the IPC buffer's pointer (result_ptr) instead
+        if self.world > 1 and self.world <= 8 and p2p is not False and dist.is_initialized() and dist.get_world_size(group) == self.world:
+            err = None
+            try:
+                self._setup_p2p()
+            except Exception as e:                      # noqa: BLE001 -- e.g. IPC not permitted in this container
+                err = e
+            ok = torch.tensor([0 if err else 1], dtype=torch.int32, device="cuda")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)          # all ranks take the same path
+            if int(ok.item()) == 1:
+                self.exchange_kind = "fused into phase A: NVLink peer stores (CUDA IPC) + one 1-element all-reduce as the barrier"
+            else:
+                self._p2p = None
+                self.p2p_error = repr(err) if err else "a peer failed to map the buffers"
+                if p2p is True:
+                    raise RuntimeError(f"peer-to-peer exchange unavailable: {self.p2p_error}")
+
+    def _setup_p2p(self):
+        """Two receive buffers per rank (alternating per transform), cudaMalloc'ed by the library and mapped into every
+        peer process with CUDA IPC; phase A then stores straight into them over NVLink."""
+        L = lib()
+        nbytes = self.recv.numel() * 8
+        own, handles = [], []
+        for _ in range(2):
+            ptr = C.c_void_p()
+            h = (C.c_uint8 * 64)()
+            _check(L.plk_ipc_alloc(nbytes, C.byref(ptr), h))
+            own.append(ptr.value)
+            handles.append(bytes(h))
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, handles, group=self.group)
+        tables, opened = [], []
+        for b in range(2):
+            arr = (C.c_void_p * self.world)()
+            for r in range(self.world):
+                if r == self.rank:
+                    arr[r] = own[b]
+                else:
+                    ptr = C.c_void_p()
+                    hb = (C.c_uint8 * 64).from_buffer_copy(gathered[r][b])
+                    _check(L.plk_ipc_open(hb, C.byref(ptr)))
+                    arr[r] = ptr.value
+                    opened.append(ptr.value)
+            tables.append(arr)
+        self._p2p = {"own": own, "tables": tables, "opened": opened, "turn": 0, "flag": torch.zeros(1, dtype=torch.int32, device="cuda")}
+
+    def close(self):
+        if self._p2p:
+            torch.cuda.synchronize()
+            if dist.is_initialized():
+                dist.barrier(group=self.group)
+            L = lib()
+            for ptr in self._p2p["opened"]:
+                L.plk_ipc_close(C.c_void_p(ptr))
+            if dist.is_initialized():
+                dist.barrier(group=self.group)
+            for ptr in self._p2p["own"]:
+                L.plk_ipc_free(C.c_void_p(ptr))
+            self._p2p = None
 
     def phase_a(self, local_rows: torch.Tensor, inverse: bool = False, rank: int = None, send: torch.Tensor = None):
         r = self.rank if rank is None else rank
@@ -194,6 +255,22 @@ class DistributedNtt:
 
     def forward(self, local_rows: torch.Tensor, inverse: bool = False) -> torch.Tensor:
         """Phase A, all-to-all (NCCL), phase B.  Returns this rank's (R1, M/G, L) slice of the output."""
+        if self._p2p:
+            # exchange fused into phase A: stores go straight into the peers' receive buffers over NVLink
+            st = self._p2p
+            b = st["turn"]
+            st["turn"] ^= 1
+            _check(lib().plk_fft_dist_phase_a_p2p(self.plan_m.handle, self.plan_n.handle, C.c_void_p(local_rows.data_ptr()), self.rows,
+                                                  self.rank * self.rows, self.world, 1 if inverse else 0, C.c_void_p(self.work.data_ptr()),
+                                                  st["tables"][b], _stream_ptr()))
+            dist.all_reduce(st["flag"], group=self.group)          # every rank's phase A has been issued and completed before phase B
+            mine = C.c_void_p(st["own"][b])
+            _check(lib().plk_fft_dist_phase_b(self.plan_n.handle, mine, self.log_r1, self.log_m - (self.world.bit_length() - 1),
+                                              1 if inverse else 0, _stream_ptr()))
+            self.result_ptr = st["own"][b]
+            if self.copy_out:
+                _check(lib().plk_copy_dev(C.c_void_p(self.recv.data_ptr()), mine, self.recv.numel() * 8, _stream_ptr()))
+            return self.recv
         self.phase_a(local_rows, inverse)
         if self.world == 1:
             self.recv.copy_(self.send.view(self.recv.shape))
@@ -204,7 +281,9 @@ class DistributedNtt:
     def check_against_single_gpu(self, local_rows: torch.Tensor, inverse: bool = False) -> bool:
         """Untimed self-check (bench.py): gather every rank's rows, run the single-GPU transform of the whole vector on
         this rank and compare this rank's output slice word for word.  -> AND over the ranks."""
+        keep, self.copy_out = self.copy_out, True
         out = self.forward(local_rows, inverse).clone()
+        self.copy_out = keep
         R1, M = 1 << self.log_r1, 1 << self.log_m
         if self.world > 1:
             full = torch.empty((R1, M, self.L), dtype=torch.int64, device="cuda")

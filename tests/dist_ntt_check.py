@@ -25,9 +25,12 @@ def main():
     rng = np.random.Generator(np.random.PCG64(1234))          # same data on every rank
     a = rng.integers(0, 1 << 62, size=(n, 4), dtype=np.uint64)
     x = torch.from_numpy(a.view(np.int64)).cuda()
-    d = DistributedNtt(pk.TWEEDLEDEE_BASE, log_n)
+    mode = os.environ.get("PLK_DIST_NTT_EXCHANGE", "p2p")
+    d = DistributedNtt(pk.TWEEDLEDEE_BASE, log_n, p2p=(False if mode == "nccl" else True))
+    if rank == 0:
+        print("exchange:", d.exchange_kind)
     rows = d.input_rows(x)
-    for inverse in (False, True):
+    for inverse in (False, True, False, True):          # twice: both receive buffers of the peer-store path
         out = d.forward(rows, inverse=inverse).clone()
         plan = pk.fft_precompute(pk.TWEEDLEDEE_BASE, n)
         want = torch.empty_like(x)
@@ -56,6 +59,7 @@ def main():
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
         print(f"domain-split NTT 2^{log_n} over {world} GPUs: {t.item():.3f} ms/transform = {n / (t.item() * 1e-3):.4g} elements/s")
+    d.close()
     dist.destroy_process_group()
 
 

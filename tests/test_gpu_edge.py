@@ -8,7 +8,7 @@ import pytest
 
 import plonky_oracle as po
 import plonky_b200 as pk
-from helpers import ints_to_limbs, limbs_to_ints, mont_array, canon_list, points_to_array, rand_scalars
+from helpers import ints_to_limbs, limbs_to_ints, mont_array, canon_list, points_to_array, rand_scalars, array_to_point
 
 pytestmark = pytest.mark.gpu
 
@@ -191,3 +191,25 @@ def test_permutation_polynomial(name, n):
         W = np.stack([mont_array(f, row) for row in w])
         with pytest.raises(pk.PlonkyPanic):
             pk.permutation_polynomial(f.fid, mont_array(f, sub), W, S, mont_array(f, k_is), mont_array(f, [beta])[0], mont_array(f, [gamma])[0])
+
+
+def test_msm_generator_of_order_two():
+    """BLS12-377 G1 has an even cofactor: T = (-1, 0) lies on y^2 = x^3 + 1 and 2 T = O.  Every higher power of T in the
+    fixed-base table is the identity; the reference handles arbitrary curve points (curve.rs:234-260 doubles through
+    y = 0 to ZERO)."""
+    c = po.BLS12_377
+    f = c.base
+    T = (f.p - 1, 0)
+    assert c.is_on_curve(T)
+    gens = [c.gen, T, c.double(c.gen), T]
+    xy, zero = points_to_array(c, gens)
+    for seed in (1, 2):
+        s = rand_scalars(c.scalar, seed, 4)
+        s[1] |= 1                       # odd multiple of T = T
+        s[3] &= ~1                      # even multiple of T = O
+        want = c.add(c.add(c.mul(s[0], gens[0]), c.mul(s[2], gens[2])), T)
+        for w in (11, 4):
+            out, oz = pk.msm_execute(pk.msm_precompute_affine(c.cid, xy, w, zero), mont_array(c.scalar, s))
+            assert not oz and array_to_point(c, out[:2], 0) == want
+        out, oz = pk.msm_parallel(c.cid, mont_array(c.scalar, s), np.concatenate([xy, np.broadcast_to(mont_array(f, [1])[0], (4, 1, f.limbs))], axis=1), 4)
+        assert not oz and array_to_point(c, out[:2], 0) == want

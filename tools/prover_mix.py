@@ -59,7 +59,17 @@ class Mix:
         self.h2d_bytes = self.vals_h.numel() * 8
 
     def mine(self, k):
-        return [i for i in range(k) if i % self.world == self.rank]
+        """this rank's contiguous block [lo, hi) of a k-item group (the split ShardedMsm uses, plonky_b200/sharding.py)"""
+        from plonky_b200.sharding import shard_range
+        return shard_range(k, self.world, self.rank)
+
+    def owner(self, k, i):
+        from plonky_b200.sharding import shard_range
+        for r in range(self.world):
+            lo, hi = shard_range(k, self.world, r)
+            if lo <= i < hi:
+                return r
+        raise IndexError(i)
 
     def group_end(self, lo, hi):
         """dependency barrier: the group's commitments reach the host (rank 0 holds all of them for N > 1)"""
@@ -84,11 +94,12 @@ class Mix:
             pkd.msm_execute_batch_dev(t, self.buf_n, self.outs[:9], self.zbytes[:9])
             pkd.fft_dev(pn, self.vals, self.buf_n, inverse=True)
         else:
-            for i in self.mine(9):
-                pkd.fft_dev(pn, self.vals[i], self.buf_n[i], inverse=True)
-                pkd.fft_dev(p8, self.buf_n[i], self.buf_8n[i])
-                pkd.msm_execute_dev(t, self.buf_n[i], self.outs[i], self.zeros[i])
-                pkd.fft_dev(pn, self.vals[i], self.buf_n[i], inverse=True)
+            lo, hi = self.mine(9)
+            if hi > lo:                   # this rank's block of the nine wires, batched like the single-GPU path
+                pkd.fft_dev(pn, self.vals[lo:hi], self.buf_n[lo:hi], inverse=True)
+                pkd.fft_dev(p8, self.buf_n[lo:hi], self.buf_8n[lo:hi])
+                pkd.msm_execute_batch_dev(t, self.buf_n[lo:hi], self.outs[lo:hi], self.zbytes[lo:hi])
+                pkd.fft_dev(pn, self.vals[lo:hi], self.buf_n[lo:hi], inverse=True)
         if not single:
             self.group_end(0, 9)
         # group 2 (Z): every rank keeps its own copy of the chain input so that group 3 can be dealt out
@@ -106,9 +117,10 @@ class Mix:
             # t chunks: dense scalars (the 8n evaluations of the chain's first transform stand in for the quotient's chunks)
             pkd.msm_execute_batch_dev(t, self.buf_8n[0, :7 * n].view(7, n, 4), self.outs[10:17], self.zbytes[10:17])
         else:
-            for i in self.mine(7):
-                pkd.msm_execute_dev(t, self.buf_8n[0, i * n:(i + 1) * n], self.outs[10 + i], self.zeros[10 + i])
-        for i in (range(8) if world == 1 else self.mine(8)):     # the remaining 8n transforms of the quotient arithmetic
+            lo, hi = self.mine(7)
+            if hi > lo:
+                pkd.msm_execute_batch_dev(t, self.buf_8n[0, lo * n:hi * n].view(hi - lo, n, 4), self.outs[10 + lo:10 + hi], self.zbytes[10 + lo:10 + hi])
+        for i in (range(8) if world == 1 else range(*self.mine(8))):     # the remaining 8n transforms of the quotient arithmetic
             pkd.fft_dev(p8, self.buf_8n[4 + i % 5], self.buf_8n[4 + (i + 1) % 5], inverse=bool(i & 1))
         if not single:
             self.group_end(10, 17)
@@ -125,7 +137,7 @@ class Mix:
         if self.world == 1:
             return self.outs.cpu().numpy().view(np.uint64).copy()
         g = self.gathered.cpu().numpy().view(np.uint64)
-        own = [i % self.world for i in range(9)] + [0] + [i % self.world for i in range(7)] + [0]
+        own = [self.owner(9, i) for i in range(9)] + [0] + [self.owner(7, i) for i in range(7)] + [0]
         return np.stack([g[own[i], i] for i in range(18)])
 
 
@@ -161,7 +173,8 @@ def bench(cx, log_n=16, reps=5, with_cpu=False):
     res = {"workload": f"prover L1 call mix, n = 2^{log_n} gates (18 MSM(n), 19 FFT(n), 13 FFT(8n)), wire values from host memory, "
                        "one D2H of the commitments per dependency group",
            "n_gpus": cx.world, "ms_per_proof_mix": ms, "proofs_per_sec": 1e3 / ms,
-           "mode": "replicas, round-robin within dependency groups" if cx.world > 1 else "single GPU, batched launches",
+           "mode": "replicas: contiguous blocks of every dependency group per rank (batched launches), the Z / quotient chain replicated" if cx.world > 1
+           else "single GPU, batched launches",
            "h2d_bytes_per_proof": m.h2d_bytes, "d2h_bytes_per_proof": 18 * 3 * 4 * 8, "timing": "host wall clock, barrier + synchronize on both sides, max over ranks",
            "launches_per_proof_rank0": int(launches)}
     # (3) N = 1: the CPU restatement of the reference on the same inputs -- parity of every commitment and the CPU time of the mix
