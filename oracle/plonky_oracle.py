@@ -820,12 +820,14 @@ def evaluate_all_constraints(field: Field, consts, local, right, below, inner_ze
 
 
 def vanishing_points(field: Field, degree: int, wires_8n, constants_8n, sigma_8n, z_8n, subgroup_8n, k_is, alpha: int, beta: int,
-                     gamma: int, inner_zeta: int, inner_a: int) -> List[int]:
-    """plonk.rs:393-452: the vanishing polynomial evaluated at the 8n points (before Polynomial::from_evaluations)."""
+                     gamma: int, inner_zeta: int, inner_a: int, indices=None) -> List[int]:
+    """plonk.rs:393-452: the vanishing polynomial evaluated at the 8n points (before Polynomial::from_evaluations);
+    `indices` restricts the evaluation to a sample of the points (the inputs are indexable by point)."""
     p = field.p
     m = 8 * degree
     out = []
-    for i, x in enumerate(subgroup_8n):
+    for i in (range(m) if indices is None else indices):
+        x = subgroup_8n[i]
         consts = [constants_8n[j][i] for j in range(NUM_CONSTANTS)]
         ir, ib = (i + 8) % m, (i + 8 * GRID_WIDTH) % m
         local = [wires_8n[j][i] for j in range(NUM_WIRES)]

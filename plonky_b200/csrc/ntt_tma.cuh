@@ -327,8 +327,14 @@ bool launch_tma_pass(const NttPassParams& p, size_t n, size_t k, cudaStream_t st
   if constexpr (F::N != 8) {
     return false;
   } else {
-  static const bool enabled = !(getenv("PLK_NTT_TMA") && atoi(getenv("PLK_NTT_TMA")) == 0);
-  if (!enabled) return false;
+  // Policy (measured on B200, 2^24 TweedledeeBase, profiles/r2_ntt_tma_ncu.txt): on full-length passes this kernel runs
+  // 4 % behind the cp.async radix-4 kernel with 8-column tiles (3.71 vs 3.55 ms per transform: half-size tiles, the tile load
+  // is not overlapped with the CTA's own butterflies); on the first pass of a zero-padded input (LDE, n_in <= n / 2) it is
+  // ahead (coset LDE 2^21 -> 2^24: 3.88 vs 3.97 ms) because the padding rows are out-of-bounds box rows the TMA engine
+  // zero-fills without memory traffic.  Default: that case only.  PLK_NTT_TMA=1 takes every qualifying pass, 0 none.
+  static const int mode = getenv("PLK_NTT_TMA") ? atoi(getenv("PLK_NTT_TMA")) : -1;
+  if (mode == 0) return false;
+  if (mode < 0 && !(p.first && p.n_in * 2 <= n)) return false;
   const int cols_log = p.first ? (p.log_n - p.r) : p.log_m;
   if (cols_log < kTmaColsLog || p.r < 1) return false;
   const unsigned R = 1u << p.r;

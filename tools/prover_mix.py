@@ -9,6 +9,7 @@
               9 x IFFT(n)                                    plonk.rs:117
     group 2   1 x IFFT(n), 1 x MSM(n)  [Z]                   plonk.rs:136-142
     group 3   1 x FFT(8n), 1 x IFFT(8n) [vanishing poly]     plonk.rs:388,455
+              vanishing_points over the 8n LDE points        plonk.rs:393-452 (ten gate evaluators, gates/mod.rs:46-125)
               divide_by_z_h: coset FFT(8n) + coset IFFT(8n)  plonk.rs:170 -> polynomial.rs:330-380
               7 x MSM(n)   [t chunks]                        plonk.rs:192
     group 4   1 x MSM(n)   [PI quotient]                     plonk.rs:231
@@ -57,6 +58,16 @@ class Mix:
         self.gathered = torch.zeros((self.world, 18, 3, 4), dtype=torch.int64, device="cuda")
         self.outs_h = torch.zeros((18, 3, 4), dtype=torch.int64).pin_memory()
         self.h2d_bytes = self.vals_h.numel() * 8
+        # inputs of the pointwise vanishing evaluation that a Circuit holds precomputed: constants_8n, s_sigma_values_8n,
+        # subgroup_8n (plonk.rs:47-63); wires_8n / Z(8n) are the LDE outputs of groups 1 and 3
+        b = rng.integers(0, 1 << 62, size=(12, 8 * n, 4), dtype=np.uint64)
+        self.consts_8n = torch.from_numpy(b[:6].view(np.int64)).cuda()
+        self.sigma_8n = torch.from_numpy(b[6:].view(np.int64)).cuda()
+        self.params = torch.from_numpy(rng.integers(0, 1 << 62, size=(11, 4), dtype=np.uint64).view(np.int64)).cuda()   # k_is[6], alpha, beta, gamma, zeta, a
+        self.subgroup_8n = torch.from_numpy(pk.fft_subgroup(self.plan_8n).view(np.int64)).cuda()
+        self.van = torch.zeros((8 * n, 4), dtype=torch.int64, device="cuda")
+        self.scr_8n = torch.zeros((5, 8 * n, 4), dtype=torch.int64, device="cuda")        # operands of the quotient arithmetic's 8n transforms
+        self.wires_8n = torch.zeros((9, 8 * n, 4), dtype=torch.int64, device="cuda")      # every rank's copy of the nine wire LDEs
 
     def mine(self, k):
         """this rank's contiguous block [lo, hi) of a k-item group (the split ShardedMsm uses, plonky_b200/sharding.py)"""
@@ -100,6 +111,12 @@ class Mix:
                 pkd.fft_dev(p8, self.buf_n[lo:hi], self.buf_8n[lo:hi])
                 pkd.msm_execute_batch_dev(t, self.buf_n[lo:hi], self.outs[lo:hi], self.zbytes[lo:hi])
                 pkd.fft_dev(pn, self.vals[lo:hi], self.buf_n[lo:hi], inverse=True)
+            # every replica needs all nine wire LDEs for the vanishing polynomial: the blocks are disjoint, so a sum over
+            # the ranks of zero-filled copies is their concatenation (one 9 x 8n x 32 B all-reduce per proof)
+            self.wires_8n.zero_()
+            if hi > lo:
+                self.wires_8n[lo:hi].copy_(self.buf_8n[lo:hi])
+            self.cx.dist.all_reduce(self.wires_8n)
         if not single:
             self.group_end(0, 9)
         # group 2 (Z): every rank keeps its own copy of the chain input so that group 3 can be dealt out
@@ -110,6 +127,14 @@ class Mix:
             self.group_end(9, 10)
         # group 3: FFT(8n), IFFT(8n), divide_by_z_h's coset pair -- a chain, replicated on every rank
         pkd.fft_dev(p8, self.buf_n[0], self.buf_8n[0])
+        # the pointwise vanishing evaluation over the 8n points (wires: the LDEs of group 1; Z: the LDE just computed)
+        import ctypes as C
+        pk = self.cx.pk
+        wires = self.buf_8n if world == 1 else self.wires_8n
+        pk._check(pk.lib().plk_vanishing_points_dev(self.field, n, C.c_void_p(wires.data_ptr()), C.c_void_p(self.consts_8n.data_ptr()),
+                                                    C.c_void_p(self.sigma_8n.data_ptr()), C.c_void_p(self.buf_8n[0].data_ptr()),
+                                                    C.c_void_p(self.subgroup_8n.data_ptr()), C.c_void_p(self.params.data_ptr()),
+                                                    C.c_void_p(self.van.data_ptr()), C.c_void_p(self.cx.torch.cuda.current_stream().cuda_stream)))
         pkd.fft_dev(p8, self.buf_8n[0], self.buf_8n[1], inverse=True)
         pkd.fft_dev(p8, self.buf_8n[1], self.buf_8n[2], coset=True)
         pkd.fft_dev(p8, self.buf_8n[2], self.buf_8n[3], inverse=True, coset=True)
@@ -121,7 +146,7 @@ class Mix:
             if hi > lo:
                 pkd.msm_execute_batch_dev(t, self.buf_8n[0, lo * n:hi * n].view(hi - lo, n, 4), self.outs[10 + lo:10 + hi], self.zbytes[10 + lo:10 + hi])
         for i in (range(8) if world == 1 else range(*self.mine(8))):     # the remaining 8n transforms of the quotient arithmetic
-            pkd.fft_dev(p8, self.buf_8n[4 + i % 5], self.buf_8n[4 + (i + 1) % 5], inverse=bool(i & 1))
+            pkd.fft_dev(p8, self.scr_8n[i % 5], self.scr_8n[(i + 1) % 5], inverse=bool(i & 1))
         if not single:
             self.group_end(10, 17)
         # group 4
@@ -162,15 +187,16 @@ def bench(cx, log_n=16, reps=5, with_cpu=False):
     checks.append("8n transform chain (FFT, IFFT, coset LDE, coset IFFT) returns the zero-padded coefficients bit for bit")
     # (2) N > 1: the replica-distributed commitments equal the single-GPU batched path on rank 0's GPU
     if cx.world > 1:
+        van_dist = m.van.clone()
         m.proof(single=True)
         torch.cuda.synchronize()
         alone = m.outs.cpu().numpy().view(np.uint64)
-        same = bool(np.array_equal(alone, got))
+        same = bool(np.array_equal(alone, got)) and bool(torch.equal(van_dist, m.van))
         t = torch.tensor([1 if (same and ok) else 0], dtype=torch.int64, device="cuda")
         cx.dist.all_reduce(t, op=cx.dist.ReduceOp.MIN)
         ok = bool(t.item())
-        checks.append("the 18 commitments gathered from the ranks == the single-GPU batched path recomputed on every rank")
-    res = {"workload": f"prover L1 call mix, n = 2^{log_n} gates (18 MSM(n), 19 FFT(n), 13 FFT(8n)), wire values from host memory, "
+        checks.append("the 18 commitments gathered from the ranks and the 8n vanishing evaluations == the single-GPU batched path recomputed on every rank")
+    res = {"workload": f"prover L1 call mix, n = 2^{log_n} gates (18 MSM(n), 19 FFT(n), 13 FFT(8n), the 8n-point vanishing evaluation), wire values from host memory, "
                        "one D2H of the commitments per dependency group",
            "n_gpus": cx.world, "ms_per_proof_mix": ms, "proofs_per_sec": 1e3 / ms,
            "mode": "replicas: contiguous blocks of every dependency group per rank (batched launches), the Z / quotient chain replicated" if cx.world > 1
@@ -181,12 +207,49 @@ def bench(cx, log_n=16, reps=5, with_cpu=False):
     if with_cpu and cx.rank == 0 and cx.world == 1:
         cpu = cpu_mix(cx, m, got)
         ok = ok and cpu.pop("ok")
-        checks.append("all 18 commitments and the 9 IFFT(n) outputs == the CPU restatement (msm_execute_parallel w=11, ifft) on the same inputs")
+        checks.append("all 18 commitments and the 9 IFFT(n) outputs == the CPU restatement (msm_execute_parallel w=11, ifft) on the same inputs; "
+                      "the vanishing evaluation at 30 sampled points of the 8n domain == the big-integer restatement of plonk.rs:393-452")
         res["cpu_baseline"] = cpu
     res["verified"] = ok
     res["verification"] = checks
     m.table.close()
     return res
+
+
+def vanishing_sample_check(cx, m, samples=24):
+    """The device's vanishing evaluation at a sample of the 8n points against the big-integer restatement of
+    plonk.rs:393-452 / gates/mod.rs:46-125 (oracle/plonky_oracle.py), on the mix's own device-resident inputs."""
+    np = cx.np
+    import plonky_oracle as po
+    f = po.FIELDS_BY_ID[m.field]
+    mm = 8 * m.n
+
+    def ints(t):            # (..., 4) int64 Montgomery limbs -> canonical python ints
+        a = t.cpu().numpy().view(np.uint64).reshape(-1, 4)
+        return [f.from_mont(sum(int(a[i, j]) << (64 * j) for j in range(4))) for i in range(a.shape[0])]
+    rng = np.random.Generator(np.random.PCG64(99))
+    idx = sorted(set([0, 1, 7, 8, mm - 8, mm - 1] + [int(v) for v in rng.integers(0, mm, size=samples)]))
+    need = sorted(set(j for i in idx for j in (i, (i + 8) % mm, (i + 8 * po.GRID_WIDTH) % mm)))
+    pos = {j: k for k, j in enumerate(need)}
+    sel = cx.torch.tensor(need, device="cuda")
+
+    class Rows:             # sparse view: rows[j][i] for the indices the sample touches
+        def __init__(self, t):
+            vals = [ints(t[r].index_select(0, sel)) for r in range(t.shape[0])]
+            self.vals = vals
+        def __getitem__(self, r):
+            outer = self
+            class Row:
+                def __getitem__(self, i):
+                    return outer.vals[r][pos[i]]
+            return Row()
+    wires, consts, sigma = Rows(m.buf_8n), Rows(m.consts_8n), Rows(m.sigma_8n)
+    zrow = Rows(m.buf_8n[0:1])[0]
+    sub = Rows(m.subgroup_8n.unsqueeze(0))[0]
+    prm = ints(m.params)
+    want = po.vanishing_points(f, m.n, wires, consts, sigma, zrow, sub, prm[:6], prm[6], prm[7], prm[8], prm[9], prm[10], indices=idx)
+    got = ints(m.van.index_select(0, cx.torch.tensor(idx, device="cuda")))
+    return got == want
 
 
 def cpu_mix(cx, m, got):
@@ -231,6 +294,7 @@ def cpu_mix(cx, m, got):
     dev_coeffs = m.buf_n.cpu().numpy().view(np.uint64)
     # buf_n holds the second IFFT(n) batch of group 1 (row 0 is overwritten identically by group 2)
     ok = ok and all(bool(np.array_equal(dev_coeffs[i], coeffs[i])) for i in range(9))
+    ok = ok and vanishing_sample_check(cx, m)
     return {"ok": ok, "value": cpu_ms, "unit": "ms per proof mix", "cores": cores, "kind": "port",
             "sample": "the same 18 MSM(n) + 19 (I)FFT(n) + 13 (I)FFT(8n) through the C++ restatement, one run, table and plans untimed"}
 
