@@ -102,6 +102,31 @@ struct XYZZ {
     o.zzz = F::mul(a.zzz, ppp);
     return o;
   }
+  // madd with six of its ten products as calls to ONE shared body each (squaring, product): the fully inlined addition is
+  // ~2500 instructions = 40 KB per loop iteration of the accumulate kernel, more than the 32 KB instruction cache level that
+  // backs the SM (ncu: no_instruction 0.94 stalls per issue); this variant keeps the loop at ~28 KB.  Same values.
+  template <bool ALL = false>
+  PLK_HD static XYZZ madd_compact(const XYZZ& a, const Affine<C>& q) {
+    if (q.is_identity()) return a;
+    if (a.is_identity()) return from_affine(q);
+    F u2 = ALL ? fp_mul_call<F>(q.x, a.zz) : F::mul(q.x, a.zz);
+    F s2 = ALL ? fp_mul_call<F>(q.y, a.zzz) : F::mul(q.y, a.zzz);
+    F p = F::sub(u2, a.x);
+    F r = F::sub(s2, a.y);
+    if (p.is_zero()) {
+      if (r.is_zero()) return dbl_affine(q);
+      return identity();
+    }
+    F pp = fp_sqr_call<F>(p);
+    F ppp = fp_mul_call<F>(p, pp);
+    F qq = fp_mul_call<F>(a.x, pp);
+    XYZZ o;
+    o.x = F::sub(F::sub(fp_sqr_call<F>(r), ppp), F::dbl(qq));
+    o.y = ALL ? F::sub(fp_mul_call<F>(r, F::sub(qq, o.x)), fp_mul_call<F>(a.y, ppp)) : F::sub(F::mul(r, F::sub(qq, o.x)), F::mul(a.y, ppp));
+    o.zz = fp_mul_call<F>(a.zz, pp);
+    o.zzz = fp_mul_call<F>(a.zzz, ppp);
+    return o;
+  }
   // a + b (value of curve_adds.rs:5-48)
   PLK_HD_NOINLINE static XYZZ add(const XYZZ& a, const XYZZ& b) {
     if (a.is_identity()) return b;

@@ -240,7 +240,7 @@ __device__ __forceinline__ XYZZ<C> load_xyzz(const void* base, size_t idx) {
 namespace plk {
 
 // one thread per task: task t of bucket b adds entries [offsets[b] + k S, min(offsets[b+1], .. + S))
-template <class C>
+template <class C, int COMPACT = 0>
 __global__ void __launch_bounds__(kAccThreads) msm_accumulate_kernel(const void* __restrict__ table, const unsigned* __restrict__ sorted,
                                                                      const unsigned* __restrict__ offsets,
                                                                      const unsigned* __restrict__ task_off, unsigned nb, unsigned task,
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(kAccThreads) msm_accumulate_kernel(const void*
       next = load_affine<C>(table, e & 0x7fffffffu);
     }
     if (negative) p.y = F::neg(p.y);
-    acc = XYZZ<C>::madd(acc, p);
+    acc = COMPACT == 2 ? XYZZ<C>::template madd_compact<true>(acc, p) : COMPACT == 1 ? XYZZ<C>::template madd_compact<false>(acc, p) : XYZZ<C>::madd(acc, p);
   }
   store_xyzz<C>(partials, t, acc);
 }
@@ -786,8 +786,16 @@ void execute_one(plk_msm_table* t, plk_msm_scratch* s, const void* d_scalars, vo
                                                                      g.task, s->partials.p);
     PLK_LAUNCHED();
   } else {
-    msm_accumulate_kernel<C><<<ablocks, kAccThreads, 0, st>>>(t->table.p, s->sorted.as<unsigned>(), s->offsets.as<unsigned>(),
-                                                              s->task_off.as<unsigned>(), g.nb, g.task, s->partials.p);
+    static const int compact = getenv("PLK_MSM_MADD_COMPACT") ? atoi(getenv("PLK_MSM_MADD_COMPACT")) : kMaddCompactDefault;   // see ec.cuh
+    if (compact == 2)
+      msm_accumulate_kernel<C, 2><<<ablocks, kAccThreads, 0, st>>>(t->table.p, s->sorted.as<unsigned>(), s->offsets.as<unsigned>(),
+                                                                   s->task_off.as<unsigned>(), g.nb, g.task, s->partials.p);
+    else if (compact == 1)
+      msm_accumulate_kernel<C, 1><<<ablocks, kAccThreads, 0, st>>>(t->table.p, s->sorted.as<unsigned>(), s->offsets.as<unsigned>(),
+                                                                   s->task_off.as<unsigned>(), g.nb, g.task, s->partials.p);
+    else
+      msm_accumulate_kernel<C, 0><<<ablocks, kAccThreads, 0, st>>>(t->table.p, s->sorted.as<unsigned>(), s->offsets.as<unsigned>(),
+                                                                   s->task_off.as<unsigned>(), g.nb, g.task, s->partials.p);
     PLK_LAUNCHED();
   }
   s->timer.mark(st);

@@ -20,6 +20,7 @@
 //   * L_1(x) = (x^n - 1) / (n (x - 1)) with x^n = w_8^(i mod 8); the 8n divisions are one table per (field, n) built with
 //     Montgomery's trick and cached (the reference recomputes a division per point).
 // One thread per point; rows are read with coalesced 32-byte loads (adjacent threads, adjacent points).
+#include <stdlib.h>
 #include <string.h>
 #include <map>
 #include <mutex>
@@ -30,6 +31,7 @@
 
 namespace plk {
 
+constexpr int kVanishDefaultMB = 4;      // measured at 2^19 points: 2.64 ms (1), 2.49 ms (3), 2.44 ms (4)
 constexpr int kVanWires = 9, kVanRouted = 6, kVanConsts = 6, kVanGridWidth = 65;
 // layout of the small constants buffer (elements of F)
 constexpr int kcK = 0, kcAlpha = 6, kcBeta = 7, kcGamma = 8, kcZetaM1 = 9, kcA = 10, kcMds = 11, kcApow = 27, kcN = 37, kcCount = 38;
@@ -114,8 +116,10 @@ __global__ void __launch_bounds__(128) vanish_l1_kernel(const void* __restrict__
   }
 }
 
-template <class P>
-__global__ void __launch_bounds__(128) vanishing_points_kernel(VanishArgs a) {
+// MB = resident CTAs per SM the register allocation is held to (1: unconstrained, 185 registers; 3: 168; 4: 128 with a few
+// hundred bytes of spills): measured variants, selected by PLK_VANISH_MB
+template <class P, int MB>
+__global__ void __launch_bounds__(128, MB) vanishing_points_kernel(VanishArgs a) {
   typedef Fp<P> F;
   const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
   const unsigned long long m = a.m;
@@ -152,11 +156,11 @@ __global__ void __launch_bounds__(128) vanishing_points_kernel(VanishArgs a) {
     acc = F::add(acc, mul(shift, AP(1)));
   }
 
-  // ---- prefix filters as a tree over the constants c0..c5 (gates/mod.rs:281-293; prefixes in the file header of mod.rs) ----
-  const F c0 = Cn(0), c1 = Cn(1);
-  const F n0 = F::sub(one, c0), n1 = F::sub(one, c1);
-  const F f_endo = mul(c0, c1), f_ra = mul(n0, n1), f_rb = mul(n0, c1), p10 = mul(c0, n1);
+  // ---- prefix filters as a tree over the constants c0..c5 (gates/mod.rs:281-293; prefixes in the file header of mod.rs).
+  // Every filter is formed right before its gate from freshly loaded constants (L1 hits) so that only the accumulator and one
+  // shared prefix stay live across the gate bodies. ----
   auto gate = [&](const F& filter, const F& weighted) { acc = F::add(acc, mul(filter, weighted)); };
+  auto notc = [&](int j) { return F::sub(one, Cn(j)); };
 
   // RescueStepAGate, prefix 00 (rescue_a.rs:37-64): constraints (root_i^5 - in_i, const_i + sum_j mds_ij root_j - out_i) interleaved
   {
@@ -172,7 +176,7 @@ __global__ void __launch_bounds__(128) vanishing_points_kernel(VanishArgs a) {
       for (int j = 0; j < 4; ++j) o = F::add(o, mul(K[kcMds + 4 * k + j], roots[j]));
       h = F::add(h, mul(F::sub(o, R(k)), AP(3 + 2 * k)));
     }
-    gate(f_ra, h);
+    gate(mul(notc(0), notc(1)), h);
   }
   // RescueStepBGate, prefix 01 (rescue_b.rs:32-56)
   {
@@ -190,7 +194,7 @@ __global__ void __launch_bounds__(128) vanishing_points_kernel(VanishArgs a) {
       for (int j = 0; j < 4; ++j) o = F::add(o, mul(K[kcMds + 4 * k + j], exps[j]));
       h = F::add(h, mul(F::sub(o, R(k)), AP(2 + k)));
     }
-    gate(f_rb, h);
+    gate(mul(notc(0), Cn(1)), h);
   }
   // CurveEndoGate, prefix 11 (curve_endo.rs:37-85)
   {
@@ -208,10 +212,11 @@ __global__ void __launch_bounds__(128) vanishing_points_kernel(VanishArgs a) {
     h = F::add(h, mul(mul(b0, F::sub(b0, one)), AP(6)));
     h = F::add(h, mul(mul(b1, F::sub(b1, one)), AP(7)));
     h = F::add(h, mul(F::sub(mul(inv, F::sub(x1, x2)), one), AP(8)));
-    gate(f_endo, h);
+    gate(mul(Cn(0), Cn(1)), h);
   }
-  const F c2 = Cn(2), c3 = Cn(3);
-  const F p100 = mul(p10, F::sub(one, c2)), p101 = mul(p10, c2);
+  const F p10 = mul(Cn(0), notc(1));
+  {
+  const F p100 = mul(p10, notc(2));
   // Base4SumGate, prefix 1000 (base_4_sum.rs:36-62)
   {
     F sum = W(0);
@@ -225,15 +230,17 @@ __global__ void __launch_bounds__(128) vanishing_points_kernel(VanishArgs a) {
       h = F::add(h, mul(prod, AP(3 + k)));
     }
     h = F::add(h, mul(F::sub(sum, W(1)), AP(2)));
-    gate(mul(p100, F::sub(one, c3)), h);
+    gate(mul(p100, notc(3)), h);
   }
   // ArithmeticGate, prefix 1001 (arithmetic.rs:35-49)
   {
     const F out = F::sub(F::add(mul(mul(Cn(4), W(0)), W(1)), mul(Cn(5), W(2))), W(3));
-    gate(mul(p100, c3), mul(out, AP(2)));
+    gate(mul(p100, Cn(3)), mul(out, AP(2)));
   }
-  const F c4 = Cn(4);
-  const F p1010 = mul(p101, F::sub(one, c3)), p1011 = mul(p101, c3);
+  }
+  const F p101 = mul(p10, Cn(2));
+  {
+  const F p1010 = mul(p101, notc(3));
   // CurveAddGate, prefix 10101 (curve_add.rs:38-81)
   {
     const F x1 = W(0), y1 = W(1), x2 = W(4), y2 = W(5), bit = W(6), inv = W(7), lam = W(8);
@@ -247,14 +254,16 @@ __global__ void __launch_bounds__(128) vanishing_points_kernel(VanishArgs a) {
     h = F::add(h, mul(F::sub(W(3), F::add(dbl(W(2)), bit)), AP(5)));
     h = F::add(h, mul(mul(bit, nb), AP(6)));
     h = F::add(h, mul(F::sub(mul(inv, F::sub(x1, x2)), one), AP(7)));
-    gate(mul(p1010, c4), h);
+    gate(mul(p1010, Cn(4)), h);
   }
   // PublicInputGate, prefix 101001 (public_input.rs:32-43); BufferGate 101000 has no constraints
   {
     F h = F::zero();
     for (int k = 0; k < 3; ++k) h = F::add(h, mul(F::sub(W(kVanRouted + k), R(k)), AP(2 + k)));
-    gate(mul(mul(p1010, F::sub(one, c4)), Cn(5)), h);
+    gate(mul(mul(p1010, notc(4)), Cn(5)), h);
   }
+  }
+  const F p1011 = mul(p101, Cn(3));
   // CurveDblGate, prefix 10111 (curve_dbl.rs:31-60)
   {
     const F xo = W(0), yo = W(1), xn = W(2), yn = W(3), inv = W(4), lam = W(5);
@@ -264,10 +273,10 @@ __global__ void __launch_bounds__(128) vanishing_points_kernel(VanishArgs a) {
     h = F::add(h, mul(F::sub(F::sub(mul(lam, lam), dbl(xo)), xn), AP(3)));
     h = F::add(h, mul(F::sub(F::sub(mul(lam, F::sub(xo, xn)), yo), yn), AP(4)));
     h = F::add(h, mul(F::sub(mul(dbl(yo), inv), one), AP(5)));
-    gate(mul(p1011, c4), h);
+    gate(mul(p1011, Cn(4)), h);
   }
   // ConstantGate, prefix 10110 (constant.rs:28-37)
-  gate(mul(p1011, F::sub(one, c4)), mul(F::sub(Cn(5), W(0)), AP(2)));
+  gate(mul(p1011, notc(4)), mul(F::sub(Cn(5), W(0)), AP(2)));
 
   store_fp<F>(a.out, i, acc);
 }
@@ -303,7 +312,11 @@ void vanishing_points_run(int field, unsigned long long degree, const void* d_wi
   }
   VanishArgs a;
   a.wires = d_wires; a.consts = d_consts; a.sigma = d_sigma; a.z = d_z; a.subgroup = d_subgroup; a.l1 = l1; a.small = small.p; a.m = m; a.out = d_out;
-  vanishing_points_kernel<P><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(a);
+  static const int mb = getenv("PLK_VANISH_MB") ? atoi(getenv("PLK_VANISH_MB")) : kVanishDefaultMB;
+  const unsigned blocks = (unsigned)((m + 127) / 128);
+  if (mb >= 4) vanishing_points_kernel<P, 4><<<blocks, 128, 0, st>>>(a);
+  else if (mb == 3) vanishing_points_kernel<P, 3><<<blocks, 128, 0, st>>>(a);
+  else vanishing_points_kernel<P, 1><<<blocks, 128, 0, st>>>(a);
   PLK_LAUNCHED();
 }
 

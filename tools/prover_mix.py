@@ -128,13 +128,7 @@ class Mix:
         # group 3: FFT(8n), IFFT(8n), divide_by_z_h's coset pair -- a chain, replicated on every rank
         pkd.fft_dev(p8, self.buf_n[0], self.buf_8n[0])
         # the pointwise vanishing evaluation over the 8n points (wires: the LDEs of group 1; Z: the LDE just computed)
-        import ctypes as C
-        pk = self.cx.pk
-        wires = self.buf_8n if world == 1 else self.wires_8n
-        pk._check(pk.lib().plk_vanishing_points_dev(self.field, n, C.c_void_p(wires.data_ptr()), C.c_void_p(self.consts_8n.data_ptr()),
-                                                    C.c_void_p(self.sigma_8n.data_ptr()), C.c_void_p(self.buf_8n[0].data_ptr()),
-                                                    C.c_void_p(self.subgroup_8n.data_ptr()), C.c_void_p(self.params.data_ptr()),
-                                                    C.c_void_p(self.van.data_ptr()), C.c_void_p(self.cx.torch.cuda.current_stream().cuda_stream)))
+        self.vanishing(self.buf_8n if world == 1 else self.wires_8n)
         pkd.fft_dev(p8, self.buf_8n[0], self.buf_8n[1], inverse=True)
         pkd.fft_dev(p8, self.buf_8n[1], self.buf_8n[2], coset=True)
         pkd.fft_dev(p8, self.buf_8n[2], self.buf_8n[3], inverse=True, coset=True)
@@ -154,6 +148,14 @@ class Mix:
             pkd.msm_execute_dev(t, self.buf_n[0], self.outs[17], self.zeros[17])
         if not single:
             self.group_end(17, 18)
+
+    def vanishing(self, wires):
+        import ctypes as C
+        pk = self.cx.pk
+        pk._check(pk.lib().plk_vanishing_points_dev(self.field, self.n, C.c_void_p(wires.data_ptr()), C.c_void_p(self.consts_8n.data_ptr()),
+                                                    C.c_void_p(self.sigma_8n.data_ptr()), C.c_void_p(self.buf_8n[0].data_ptr()),
+                                                    C.c_void_p(self.subgroup_8n.data_ptr()), C.c_void_p(self.params.data_ptr()),
+                                                    C.c_void_p(self.van.data_ptr()), C.c_void_p(self.cx.torch.cuda.current_stream().cuda_stream)))
 
     def commitments(self):
         """(18, 3, 4) uint64 on the host: for N > 1 item i comes from the rank that owns it"""
@@ -180,6 +182,16 @@ def bench(cx, log_n=16, reps=5, with_cpu=False):
     ms = cx.max_over_ranks((time.perf_counter() - t0) * 1e3 / reps)
     launches = (pk.kernel_launch_count() - l0) // reps
     got = m.commitments()
+    # the vanishing evaluation alone (device resident, CUDA events)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wires = m.buf_8n if cx.world == 1 else m.wires_8n
+    m.vanishing(wires)
+    e0.record()
+    for _ in range(5):
+        m.vanishing(wires)
+    e1.record()
+    torch.cuda.synchronize()
+    van_ms = e0.elapsed_time(e1) / 5
     checks = []
     # (1) the chain FFT(8n) -> IFFT(8n) -> coset LDE -> coset IFFT is the identity on the zero-padded coefficients
     n = m.n
@@ -202,7 +214,9 @@ def bench(cx, log_n=16, reps=5, with_cpu=False):
            "mode": "replicas: contiguous blocks of every dependency group per rank (batched launches), the Z / quotient chain replicated" if cx.world > 1
            else "single GPU, batched launches",
            "h2d_bytes_per_proof": m.h2d_bytes, "d2h_bytes_per_proof": 18 * 3 * 4 * 8, "timing": "host wall clock, barrier + synchronize on both sides, max over ranks",
-           "launches_per_proof_rank0": int(launches)}
+           "launches_per_proof_rank0": int(launches),
+           "vanishing_points_ms": van_ms, "vanishing_points_per_sec": 8 * m.n / (van_ms * 1e-3),
+           "vanishing_note": "plk_vanishing_points_dev over the 8n = 2^19 points alone: 24 rows x 32 B read + 32 B written and ~230 Montgomery products per point"}
     # (3) N = 1: the CPU restatement of the reference on the same inputs -- parity of every commitment and the CPU time of the mix
     if with_cpu and cx.rank == 0 and cx.world == 1:
         cpu = cpu_mix(cx, m, got)
