@@ -42,6 +42,15 @@ extern "C" {
     fn plk_blake_hash_usize_to_curve(curve: c_int, seed_start: u64, n: usize, points_xy: *mut u64) -> c_int;
     fn plk_points_compress(curve: c_int, points_xy: *const u64, zero: *const u8, n: usize, out: *mut u8) -> c_int;
     fn plk_points_decompress(curve: c_int, input: *const u8, n: usize, out_xy: *mut u64, out_zero: *mut u8, out_status: *mut u8) -> c_int;
+    // round 2: one-call blinded commitments (src/poly_commit.rs:32-66), vanishing_poly (src/plonk.rs:375-456), field bytes, subgroup
+    fn plk_commit_batch(t: *const plk_msm_table, scalars: *const u64, n: usize, k: usize, blinding: *const u64, h_xy: *const u64, h_zero: u8,
+                        out_xy: *mut u64, out_zero: *mut u8) -> c_int;
+    fn plk_vanishing_poly(plan_8n: *const plk_fft_plan, degree: usize, wires_8n: *const u64, constants_8n: *const u64, sigma_8n: *const u64,
+                          plonk_z_coeffs: *const u64, k_is: *const u64, alpha: *const u64, beta: *const u64, gamma: *const u64,
+                          inner_zeta: *const u64, inner_a: *const u64, out_coeffs_8n: *mut u64) -> c_int;
+    fn plk_field_to_bytes(field: c_int, input: *const u64, n: usize, out: *mut u8) -> c_int;
+    fn plk_field_from_bytes(field: c_int, input: *const u8, n: usize, out: *mut u64) -> c_int;
+    fn plk_fft_subgroup(p: *const plk_fft_plan, out: *mut u64) -> c_int;
 }
 
 /// The reference panics on this path (assert_eq! curve_msm.rs:67,106; log2_strict util.rs:16-19;
@@ -231,6 +240,35 @@ pub fn gpu_pedersen_generators<C: GpuCurve>(start: usize, n: usize) -> Vec<u64> 
     xy          // n x (x, y) Montgomery limbs; AffinePoint::nonzero(x, y) each
 }
 
+/// body of PolynomialCommitment::coeffs_vec_to_commitments (poly_commit.rs:52-66): k MSMs + [blinding_i] H + batch_to_affine, one call
+pub fn gpu_commit_batch<C: GpuCurve>(table: *const plk_msm_table, rows: &[&[C::ScalarField]], blinding: Option<&[C::ScalarField]>,
+                                     h: &AffinePoint<C>) -> Vec<AffinePoint<C>>
+where C::BaseField: GpuField, C::ScalarField: GpuField {
+    let (k, n, l) = (rows.len(), rows[0].len(), C::BaseField::LIMBS);
+    let scalars: Vec<u64> = rows.iter().flat_map(|r| r.iter().flat_map(|x| x.limbs().iter().copied())).collect();
+    let blind: Option<Vec<u64>> = blinding.map(|b| b.iter().flat_map(|x| x.limbs().iter().copied()).collect());
+    let mut hxy = Vec::with_capacity(2 * l);
+    hxy.extend_from_slice(h.x.limbs());
+    hxy.extend_from_slice(h.y.limbs());
+    let (mut out, mut zero) = (vec![0u64; k * 2 * l], vec![0u8; k]);
+    check(unsafe { plk_commit_batch(table, scalars.as_ptr(), n, k, blind.as_ref().map_or(std::ptr::null(), |b| b.as_ptr()), hxy.as_ptr(),
+                                    h.zero as u8, out.as_mut_ptr(), zero.as_mut_ptr()) });
+    (0..k).map(|i| if zero[i] != 0 { AffinePoint::ZERO } else {
+        AffinePoint::nonzero(C::BaseField::from_limbs(&out[2 * l * i..2 * l * i + l]), C::BaseField::from_limbs(&out[2 * l * i + l..2 * l * (i + 1)])) }).collect()
+}
+
+/// body of Circuit::vanishing_poly (plonk.rs:375-456): rows are the 8n-point evaluations the circuit already holds
+pub fn gpu_vanishing_poly<F: GpuField>(plan_8n: *const plk_fft_plan, degree: usize, wires_8n: &[Vec<F>], constants_8n: &[Vec<F>],
+                                       sigma_8n: &[Vec<F>], z_coeffs: &[F], k_is: &[F], alpha: F, beta: F, gamma: F, zeta: F, a: F) -> Vec<F> {
+    let rows = |m: &[Vec<F>]| -> Vec<u64> { m.iter().flat_map(|r| r.iter().flat_map(|x| x.limbs().iter().copied())).collect() };
+    let flat = |v: &[F]| -> Vec<u64> { v.iter().flat_map(|x| x.limbs().iter().copied()).collect() };
+    let (w, c, s, z, k) = (rows(wires_8n), rows(constants_8n), rows(sigma_8n), flat(z_coeffs), flat(k_is));
+    let mut out = vec![0u64; 8 * degree * F::LIMBS];
+    check(unsafe { plk_vanishing_poly(plan_8n, degree, w.as_ptr(), c.as_ptr(), s.as_ptr(), z.as_ptr(), k.as_ptr(), alpha.limbs().as_ptr(),
+                                      beta.limbs().as_ptr(), gamma.limbs().as_ptr(), zeta.limbs().as_ptr(), a.limbs().as_ptr(), out.as_mut_ptr()) });
+    out.chunks(F::LIMBS).map(F::from_limbs).collect()
+}
+
 // ---- edits in the reference -----------------------------------------------------------------------
 // src/curve/curve_msm.rs
 //   pub struct MsmPrecomputation<C> { generators: Vec<ProjectivePoint<C>>, w: usize, #[serde(skip)] gpu: OnceCell<GpuTable> }
@@ -249,3 +287,7 @@ pub fn gpu_pedersen_generators<C: GpuCurve>(start: usize, n: usize) -> Vec<u64> 
 //                         after the challenge: ipa.fold(u_j, u_j_inv); at the end plk_ipa_read gives halo_a[0], halo_b[0], halo_g
 // src/circuit_builder.rs:1127, src/verifier.rs:174   pedersen_g -> gpu::gpu_pedersen_generators::<C>(0, degree)
 // src/serialization.rs:32-72   Vec<AffinePoint<C>> (de)serialisation of proofs / VKs -> plk_points_compress / plk_points_decompress
+// src/serialization.rs:17-30   Field ToBytes / FromBytes over slices -> plk_field_to_bytes / plk_field_from_bytes
+// src/poly_commit.rs:52-66     coeffs_vec_to_commitments -> gpu::gpu_commit_batch (the caller draws the blinding factors, :39-43)
+// src/plonk.rs:375-456         vanishing_poly -> gpu::gpu_vanishing_poly(self.fft_precomputation_8n plan, ..., InnerC::ZETA, InnerC::A)
+// src/plonk.rs:47-51           subgroup_n / subgroup_8n -> plk_fft_subgroup
