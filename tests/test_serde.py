@@ -151,3 +151,43 @@ def test_coeffs_vec_to_commitments(name, blinding):
         assert (None if oz[i] else array_to_point(c, out[i], 0)) == want
     if not blinding:
         assert oz[3] and not out[3].any()
+
+
+@pytest.mark.gpu
+def test_new_entry_points_error_paths():
+    """status codes instead of aborts on the round-2 entry points (the reference panics / returns io::Error here)"""
+    import plonky_b200 as pk
+    c = po.TWEEDLEDEE
+    f = c.scalar
+    g = pk.blake_hash_usize_to_curve(c.cid, 0, 9)
+    pre = pk.msm_precompute_affine(c.cid, g[:8], 11)
+    coeffs = np.stack([mont_array(f, rand_scalars(f, 1, 8))])
+    # commit: scalars.len() != precomputation.len() is the reference's assert_eq! (curve_msm.rs:106)
+    with pytest.raises(pk.PlonkyPanic):
+        pk.coeffs_vec_to_commitments(coeffs[:, :7], pre, g[8])
+    # commit with the blinding point at infinity: the blinding term vanishes
+    out, oz = pk.coeffs_vec_to_commitments(coeffs, pre, np.zeros((2, 4), dtype=np.uint64), mont_array(f, [5]), blinding_point_zero=True)
+    plain, pz = pk.msm_execute(pre, coeffs[0])
+    assert not oz[0] and np.array_equal(out[0], plain[:2])
+    # vanishing_poly: non power-of-two degree = log2_strict panic; unknown field = EINVAL
+    with pytest.raises(pk.PlonkyPanic):
+        pk.vanishing_points(f.fid, 6, np.zeros((9, 48, 4), np.uint64), np.zeros((6, 48, 4), np.uint64), np.zeros((6, 48, 4), np.uint64),
+                            np.zeros((48, 4), np.uint64), np.zeros((48, 4), np.uint64), np.zeros((6, 4), np.uint64), *[np.zeros((1, 4), np.uint64)] * 5)
+    with pytest.raises(ValueError):
+        pk.lib()  # keep the library loaded
+        pk._check(pk.lib().plk_vanishing_points(3, 8, *[None] * 12))
+    # field bytes: wrong field id, and the all-ones pattern (>= p) is "Out of range"
+    with pytest.raises(ValueError):
+        pk.field_from_bytes(f.fid, np.full((1, 32), 0xFF, dtype=np.uint8))
+    # degree-1 vanishing evaluation (8 points): L_1 == 1 everywhere on the trivial subgroup {1}
+    deg = 1
+    rows = lambda k, seed: np.stack([mont_array(f, rand_scalars(f, seed + j, 8)) for j in range(k)])
+    pre8 = pk.fft_precompute(f.fid, 8)
+    sub = pk.fft_subgroup(pre8)
+    wires, consts, sigma, z = rows(9, 10), rows(6, 30), rows(6, 50), mont_array(f, rand_scalars(f, 70, 8))
+    small = [mont_array(f, rand_scalars(f, 80 + j, 6 if j == 0 else 1)) for j in range(6)]
+    got = pk.vanishing_points(f.fid, deg, wires, consts, sigma, z, sub, *small)
+    C = lambda a: [f.from_mont(v) for v in limbs_to_ints(a)]
+    want = po.vanishing_points(f, deg, [C(w) for w in wires], [C(w) for w in consts], [C(w) for w in sigma], C(z), C(sub), C(small[0]),
+                               *[C(s)[0] for s in small[1:]])
+    assert C(got) == want
