@@ -78,38 +78,49 @@ __global__ void vanish_setup_kernel(const Fp<P>* __restrict__ in, unsigned long 
   out[kcN] = F::from_canonical(nn);
 }
 
-// L_1(x_i) for the m = 8n points (plonk_util.rs:14-24), strips of 16 points per thread share one inversion
+// L_1(x_i) for the m = 8n points x_i = w^i of the field's OWN 8n-th root of unity w (plonk_util.rs:14-24): the cached table
+// must not depend on the subgroup array a caller hands in.  Strips of 16 points per thread share one inversion; a thread's
+// first point w^(16 t) comes from binary powering, the others from successive products.
 template <class P>
-__global__ void __launch_bounds__(128) vanish_l1_kernel(const void* __restrict__ subgroup, unsigned long long m, const Fp<P>* __restrict__ small,
-                                                        void* __restrict__ out) {
+__global__ void __launch_bounds__(128) vanish_l1_kernel(Fp<P> w, unsigned long long m, const Fp<P>* __restrict__ small, void* __restrict__ out) {
   typedef Fp<P> F;
   constexpr int S = 16;
   const unsigned long long t = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
   const unsigned long long lo = t * S;
   if (lo >= m) return;
   const F one = F::one(), n = small[kcN];
+  F x0 = one, b = w;                                  // x0 = w^lo
+  for (unsigned long long e = lo; e; e >>= 1) {
+    if (e & 1) x0 = vmul<F>(x0, b);
+    b = vmul<F>(b, b);
+  }
+  F w8 = w;                                           // w^(m/8): the primitive 8th root, x^n = w8^(i mod 8)
+  for (unsigned long long e = m >> 3; e > 1; e >>= 1) w8 = vmul<F>(w8, w8);
   F pre[S];
-  F run = one;
+  F run = one, x = x0;
   for (int k = 0; k < S; ++k) {
-    const unsigned long long i = lo + k;
     pre[k] = run;
-    if (i < m) {
-      const F x = load_fp<F>(subgroup, i);
+    if (lo + k < m) {
       const F d = (x == one) ? one : vmul<F>(n, F::sub(x, one));
       run = vmul<F>(run, d);
+      x = vmul<F>(x, w);
     }
   }
   F inv = F::inverse(run);
+  // x^n for the last point of the strip, then walk both down: x /= w is x * w^-1 -- avoided by recomputing from x0 instead
+  F xs[S];
+  x = x0;
+  for (int k = 0; k < S; ++k) { xs[k] = x; x = vmul<F>(x, w); }
   for (int k = S - 1; k >= 0; --k) {
     const unsigned long long i = lo + k;
     if (i >= m) continue;
-    const F x = load_fp<F>(subgroup, i);
     F r;
-    if (x == one) r = one;
+    if (xs[k] == one) r = one;
     else {
       const F dinv = vmul<F>(inv, pre[k]);
-      inv = vmul<F>(inv, vmul<F>(n, F::sub(x, one)));
-      const F xn = load_fp<F>(subgroup, (i & 7) * (m >> 3));       // x^n = w_8^(i mod 8) = subgroup[(i mod 8) * m / 8]
+      inv = vmul<F>(inv, vmul<F>(n, F::sub(xs[k], one)));
+      F xn = one;                                     // w8^(i mod 8)
+      for (unsigned j = 0; j < (unsigned)(i & 7); ++j) xn = vmul<F>(xn, w8);
       r = vmul<F>(F::sub(xn, one), dinv);
     }
     store_fp<F>(out, i, r);
@@ -290,6 +301,7 @@ void vanishing_points_run(int field, unsigned long long degree, const void* d_wi
                           const void* d_subgroup, const void* d_params /* 11 elements */, void* d_out, cudaStream_t st) {
   typedef Fp<P> F;
   const unsigned long long m = 8 * degree;
+  if (log2_floor(m) > P::TWO_ADICITY) fail(PLK_ETOOBIG, "log2(8 * degree) exceeds TWO_ADICITY");      // field.rs:430
   int dev = 0;
   PLK_CUDA(cudaGetDevice(&dev));
   DevBuf small(kcCount * sizeof(F), st);
@@ -303,7 +315,10 @@ void vanishing_points_run(int field, unsigned long long degree, const void* d_wi
     if (it == g_l1_tables.end()) {
       auto* buf = new DevBuf(m * sizeof(F));
       const unsigned long long threads = (m + 15) / 16;
-      vanish_l1_kernel<P><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(d_subgroup, m, small.as<F>(), buf->p);
+      F w;
+      const uint32_t* wl = FieldTables<P>::root(log2_floor(m));      // primitive_root_of_unity(log2(8n)), field.rs:429-435
+      for (int i = 0; i < F::N; ++i) w.l[i] = wl[i];
+      vanish_l1_kernel<P><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(w, m, small.as<F>(), buf->p);
       PLK_LAUNCHED();
       PLK_CUDA(cudaStreamSynchronize(st));          // the table outlives this stream's ordering
       it = g_l1_tables.emplace(key, buf).first;
