@@ -147,3 +147,27 @@ def test_msm_full_size_pedersen_g_vs_port(name, logn):
     out, oz = pk.msm_execute_parallel(pk.msm_precompute_affine(c.cid, g, 11), S)
     want_xy, want_zero = rp.MsmTable(c.cid, g, None, 11).execute(S, parallel=True)
     assert oz == want_zero and np.array_equal(out[:2], want_xy)
+
+
+def test_ntt_four_pass_size_properties():
+    """2^25 over TweedledumBase (the prover's field for Circuit<Tweedledee>): the smallest size that needs FOUR passes
+    (digits 7, 6, 6, 6).  Round trip bit for bit, spot values of a sparse input against big integers, linearity."""
+    f = po.TWEEDLEDUM_BASE
+    logn = 25
+    n = 1 << logn
+    pre = pk.fft_precompute(f.fid, n)
+    x = rand_limbs(n, 25)
+    X = pk.fft_with_precomputation_power_of_2(x, pre)
+    assert np.array_equal(pk.ifft_with_precomputation_power_of_2(X, pre), x)
+    sp = np.zeros((n, 4), dtype=np.uint64)
+    idx = [0, 1, 127, 128, 8191, 8192, n // 2 + 3, n - 1]          # digit borders of the 7 / 6 / 6 / 6 split
+    vals = [3, 5, 7, 11, 13, 17, 19, 23]
+    for j, v in zip(idx, vals):
+        sp[j] = mont_array(f, [v])[0]
+    SP = pk.fft_with_precomputation_power_of_2(sp, pre)
+    w = f.primitive_root_of_unity(logn)
+    for k in (0, 1, 63, 64, 4095, 4096, 262143, 262144, n // 3, n - 1):
+        want = sum(v * pow(w, j * k, f.p) for j, v in zip(idx, vals)) % f.p
+        assert canon_list(f, SP[k:k + 1]) == [want]
+    XS = pk.fft_with_precomputation_power_of_2(pk.field_op(f.fid, "add", x, sp), pre)
+    assert np.array_equal(XS, pk.field_op(f.fid, "add", X, SP))
