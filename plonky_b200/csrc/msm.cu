@@ -75,7 +75,7 @@ plk_msm_scratch* scratch_for(plk_msm_table* t, cudaStream_t st) {
     s->affine_rounds = g.affine_rounds;
     if (t->temporary)
       for (plk::DevBuf* b : {&s->counts, &s->offsets, &s->task_off, &s->cursors, &s->sorted, &s->partials, &s->buckets, &s->ranges, &s->big_list,
-                             &s->cta_hist})
+                             &s->cta_hist, &s->chunks[0], &s->chunks[1]})
         b->set_async(st);
     try {
       s->counts.alloc((size_t)g.nb * 4);
@@ -86,7 +86,9 @@ plk_msm_scratch* scratch_for(plk_msm_table* t, cudaStream_t st) {
       s->partials.alloc(t->max_tasks * xyzz);
       s->buckets.alloc((size_t)g.nb * xyzz);
       s->ranges.alloc(((size_t)g.nb / kRangeSize + 1) * xyzz);
-      s->big_list.alloc(((size_t)g.nb + 1) * 4);
+      s->big_list.alloc(((size_t)g.nb + 1 + plk::kPartsMax) * 4);        // one list (count + entries) per part of the overlapped pipeline
+      if (!g.variable && !t->temporary)
+        for (auto& cb : s->chunks) cb.alloc(((size_t)g.nb / kRangeSize / 2 + plk::kPartsMax + 16) * xyzz);
       if (g.affine_rounds > 0) {
         // round r leaves at most entries / 2^r + nb points (every bucket rounds up)
         const size_t t1 = (entries >> 1) + g.nb + 1, t2 = (entries >> 2) + g.nb + 1;

@@ -241,38 +241,42 @@ namespace plk {
 
 // one thread per task: task t of bucket b adds entries [offsets[b] + k S, min(offsets[b+1], .. + S))
 template <class C, int COMPACT = 0>
-__global__ void __launch_bounds__(kAccThreads) msm_accumulate_kernel(const void* __restrict__ table, const unsigned* __restrict__ sorted,
+__global__ void __launch_bounds__(kAccThreads, (Fp<typename C::Base>::N <= 8 ? 4 : 1)) msm_accumulate_kernel(const void* __restrict__ table, const unsigned* __restrict__ sorted,
                                                                      const unsigned* __restrict__ offsets,
-                                                                     const unsigned* __restrict__ task_off, unsigned nb, unsigned task,
-                                                                     void* __restrict__ partials) {
+                                                                     const unsigned* __restrict__ task_off, unsigned b_lo, unsigned b_hi,
+                                                                     unsigned task, void* __restrict__ partials) {
   typedef Fp<typename C::Base> F;
-  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned total = task_off[nb];
-  if (t >= total) return;
-  // bucket of task t: last b with task_off[b] <= t
-  unsigned lo = 0, hi = nb;
-  while (hi - lo > 1) {
-    unsigned mid = (lo + hi) >> 1;
-    if (task_off[mid] <= t) lo = mid; else hi = mid;
-  }
-  const unsigned b = lo;
-  const unsigned start = offsets[b] + (t - task_off[b]) * task;
-  unsigned end = offsets[b + 1];
-  if (end > start + task) end = start + task;
-  XYZZ<C> acc = XYZZ<C>::identity();
-  unsigned e = sorted[start];
-  Affine<C> next = load_affine<C>(table, e & 0x7fffffffu);
-  for (unsigned k = start; k < end; ++k) {
-    Affine<C> p = next;
-    const bool negative = (e >> 31) != 0;
-    if (k + 1 < end) {
-      e = sorted[k + 1];
-      next = load_affine<C>(table, e & 0x7fffffffu);
+  // the tasks of buckets [b_lo, b_hi): the whole bucket set in one launch, or one part of the overlapped pipeline.
+  // Grid-stride: a part's grid is sized for an even share of the tasks (its exact count is only known on the device);
+  // a skewed digit distribution makes some threads take a second task instead of making the launch carry thousands
+  // of CTAs that exit at once (each of those still waits for a register-file slot behind the working CTAs).
+  const unsigned tend = task_off[b_hi];
+  for (unsigned t = task_off[b_lo] + blockIdx.x * blockDim.x + threadIdx.x; t < tend; t += gridDim.x * blockDim.x) {
+    // bucket of task t: last b with task_off[b] <= t
+    unsigned lo = b_lo, hi = b_hi;
+    while (hi - lo > 1) {
+      unsigned mid = (lo + hi) >> 1;
+      if (task_off[mid] <= t) lo = mid; else hi = mid;
     }
-    if (negative) p.y = F::neg(p.y);
-    acc = COMPACT == 2 ? XYZZ<C>::template madd_compact<true>(acc, p) : COMPACT == 1 ? XYZZ<C>::template madd_compact<false>(acc, p) : XYZZ<C>::madd(acc, p);
+    const unsigned b = lo;
+    const unsigned start = offsets[b] + (t - task_off[b]) * task;
+    unsigned end = offsets[b + 1];
+    if (end > start + task) end = start + task;
+    XYZZ<C> acc = XYZZ<C>::identity();
+    unsigned e = sorted[start];
+    Affine<C> next = load_affine<C>(table, e & 0x7fffffffu);
+    for (unsigned k = start; k < end; ++k) {
+      Affine<C> p = next;
+      const bool negative = (e >> 31) != 0;
+      if (k + 1 < end) {
+        e = sorted[k + 1];
+        next = load_affine<C>(table, e & 0x7fffffffu);
+      }
+      if (negative) p.y = F::neg(p.y);
+      acc = COMPACT == 2 ? XYZZ<C>::template madd_compact<true>(acc, p) : COMPACT == 1 ? XYZZ<C>::template madd_compact<false>(acc, p) : XYZZ<C>::madd(acc, p);
+    }
+    store_xyzz<C>(partials, t, acc);
   }
-  store_xyzz<C>(partials, t, acc);
 }
 
 // The three tail kernels below run one QUAD (4 lanes) per logical work item, see QuadXYZZ in ec.cuh.
@@ -282,12 +286,12 @@ __global__ void __launch_bounds__(kAccThreads) msm_accumulate_kernel(const void*
 // (Measured alternatives at 2^15 buckets x 16 partials: one thread per bucket 0.20 ms; four lanes with quad-mask
 // shuffles 0.27 ms; one QuadXYZZ quad per bucket 0.27 ms.)
 template <class C>
-__global__ void __launch_bounds__(128) msm_bucket_sum_kernel(const void* __restrict__ partials, const unsigned* __restrict__ task_off, unsigned nb,
-                                                            void* __restrict__ buckets, unsigned* __restrict__ big_list) {
+__global__ void __launch_bounds__(128) msm_bucket_sum_kernel(const void* __restrict__ partials, const unsigned* __restrict__ task_off, unsigned b_lo,
+                                                            unsigned b_hi, void* __restrict__ buckets, unsigned* __restrict__ big_list) {
   typedef Fp<typename C::Base> F;
   const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned b = gid >> 1, h = gid & 1;
-  const bool valid = b < nb;
+  const unsigned b = b_lo + (gid >> 1), h = gid & 1;
+  const bool valid = b < b_hi;
   const unsigned t0 = valid ? task_off[b] : 0u, t1 = valid ? task_off[b + 1] : 0u;
   const bool big = t1 - t0 > kBigBucket;            // skewed digit distribution: leave it to msm_big_bucket_kernel
   XYZZ<C> acc = XYZZ<C>::identity();
@@ -334,12 +338,12 @@ __global__ void __launch_bounds__(256) msm_big_bucket_kernel(const void* __restr
 // bucket index b carries weight (b + 1).  Range [lo, lo + R): sum_b (b + 1) B_b =
 //   sum_b (b - lo + 1) B_b  (running sum, curve_msm.rs:149-154)  +  lo * sum_b B_b
 template <class C>
-__global__ void __launch_bounds__(kQuadThreads) msm_range_kernel(const void* __restrict__ buckets, unsigned nb, unsigned nbw,
+__global__ void __launch_bounds__(kQuadThreads) msm_range_kernel(const void* __restrict__ buckets, unsigned r_lo, unsigned nb, unsigned nbw,
                                                                 void* __restrict__ range_out) {
   typedef QuadXYZZ<C> Q;
   __shared__ uint4 quad_sm[(kQuadThreads / 4) * Q::kSmemVec];
   typename Q::Ctx qc = Q::make_ctx(quad_sm);
-  const unsigned r = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  const unsigned r = r_lo + ((blockIdx.x * blockDim.x + threadIdx.x) >> 2);   // ranges r_lo .. ceil(nb / R) - 1
   const unsigned lo = r * kRangeSize;
   if (lo >= nb) return;
   unsigned hi = lo + kRangeSize;
@@ -787,26 +791,114 @@ void execute_one(plk_msm_table* t, plk_msm_scratch* s, const void* d_scalars, vo
     PLK_LAUNCHED();
   } else {
     static const int compact = getenv("PLK_MSM_MADD_COMPACT") ? atoi(getenv("PLK_MSM_MADD_COMPACT")) : kMaddCompactDefault;   // see ec.cuh
-    if (compact == 2)
-      msm_accumulate_kernel<C, 2><<<ablocks, kAccThreads, 0, st>>>(t->table.p, s->sorted.as<unsigned>(), s->offsets.as<unsigned>(),
-                                                                   s->task_off.as<unsigned>(), g.nb, g.task, s->partials.p);
-    else if (compact == 1)
-      msm_accumulate_kernel<C, 1><<<ablocks, kAccThreads, 0, st>>>(t->table.p, s->sorted.as<unsigned>(), s->offsets.as<unsigned>(),
-                                                                   s->task_off.as<unsigned>(), g.nb, g.task, s->partials.p);
-    else
-      msm_accumulate_kernel<C, 0><<<ablocks, kAccThreads, 0, st>>>(t->table.p, s->sorted.as<unsigned>(), s->offsets.as<unsigned>(),
-                                                                   s->task_off.as<unsigned>(), g.nb, g.task, s->partials.p);
-    PLK_LAUNCHED();
+    auto accumulate = [&](cudaStream_t q, unsigned b_lo, unsigned b_hi, unsigned ablocks) {
+      if (compact == 2)
+        msm_accumulate_kernel<C, 2><<<ablocks, kAccThreads, 0, q>>>(t->table.p, s->sorted.as<unsigned>(), s->offsets.as<unsigned>(),
+                                                                    s->task_off.as<unsigned>(), b_lo, b_hi, g.task, s->partials.p);
+      else if (compact == 1)
+        msm_accumulate_kernel<C, 1><<<ablocks, kAccThreads, 0, q>>>(t->table.p, s->sorted.as<unsigned>(), s->offsets.as<unsigned>(),
+                                                                    s->task_off.as<unsigned>(), b_lo, b_hi, g.task, s->partials.p);
+      else
+        msm_accumulate_kernel<C, 0><<<ablocks, kAccThreads, 0, q>>>(t->table.p, s->sorted.as<unsigned>(), s->offsets.as<unsigned>(),
+                                                                    s->task_off.as<unsigned>(), b_lo, b_hi, g.task, s->partials.p);
+      PLK_LAUNCHED();
+    };
+    const int parts = s->parts_for(g, t->temporary);
+    if (parts > 1) {
+      // Overlapped pipeline (opt-in, PLK_MSM_OVERLAP_PARTS; see parts_for for why it is not the default).  The bucket set
+      // is cut into `parts` equal ranges; the accumulate kernels of the ranges run on streams of descending priority
+      // (PLK_MSM_OVERLAP_MODE=1: back to back on the caller's stream), and as soon as one range is accumulated its
+      // reduction tail -- bucket_sum, big buckets, running sums, chunk sums -- runs on the highest-priority stream
+      // underneath the accumulation of the following ranges; only the last range's tail and the final tree stay exposed.
+      // PLK_MSM_OVERLAP_TRACE=1 prints when each part's accumulation and tail finished (profiles/r2_msm_overlap_trace.txt).
+      s->ensure_streams(parts);
+      const unsigned per = g.nb / parts, rper = per / kRangeSize;
+      const unsigned part_blocks = ablocks / parts + ablocks / (32 * parts) + 1;      // an even share + 3 %; the kernel strides over any excess
+      PLK_CUDA(cudaMemsetAsync(s->big_list.p, 0, ((size_t)g.nb + 1 + kPartsMax) * 4, st));
+      PLK_CUDA(cudaEventRecord(s->fork_ev, st));
+      static const bool trace = getenv("PLK_MSM_OVERLAP_TRACE") != nullptr;
+      static cudaEvent_t tr0, tr_acc[kPartsMax], tr_tail[kPartsMax];
+      static bool tr_made = false;
+      if (trace && !tr_made) {
+        cudaEventCreate(&tr0);
+        for (int i = 0; i < kPartsMax; ++i) { cudaEventCreate(&tr_acc[i]); cudaEventCreate(&tr_tail[i]); }
+        tr_made = true;
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        fprintf(stderr, "[trace] stream priority range least=%d greatest=%d\n", least, greatest);
+      }
+      if (trace) cudaEventRecord(tr0, st);
+      unsigned out_per = 0;
+      const void* last = nullptr;
+      for (int k = 0; k < parts; ++k) {
+        const unsigned b_lo = k * per, b_hi = b_lo + per;
+        static const int same_stream = getenv("PLK_MSM_OVERLAP_MODE") ? atoi(getenv("PLK_MSM_OVERLAP_MODE")) : 0;
+        cudaStream_t q = same_stream ? st : s->part_st[k];
+        if (!same_stream) PLK_CUDA(cudaStreamWaitEvent(q, s->fork_ev, 0));
+        accumulate(q, b_lo, b_hi, part_blocks);
+        PLK_CUDA(cudaEventRecord(s->acc_ev[k], q));
+        if (trace) cudaEventRecord(tr_acc[k], q);
+        cudaStream_t ts = s->tail_st;
+        PLK_CUDA(cudaStreamWaitEvent(ts, s->acc_ev[k], 0));
+        unsigned* list = s->big_list.as<unsigned>() + b_lo + k;            // per - 1 slots + the count: one list per part
+        msm_bucket_sum_kernel<C><<<(2 * per + 127) / 128, 128, 0, ts>>>(s->partials.p, s->task_off.as<unsigned>(), b_lo, b_hi, s->buckets.p, list);
+        PLK_LAUNCHED();
+        // every tail CTA must fit the hole ONE retiring accumulate CTA leaves (128 threads x 128 registers): a larger CTA
+        // is never placed while the accumulation of the next part keeps refilling the register file, and the whole
+        // tail chain waits behind it (measured: 256-thread big-bucket CTAs serialised the tails after the accumulation)
+        msm_big_bucket_kernel<C><<<16, 128, 128 * xyzz, ts>>>(s->partials.p, s->task_off.as<unsigned>(), s->buckets.p, list);
+        PLK_LAUNCHED();
+        msm_range_kernel<C><<<(4 * rper + kQuadThreads - 1) / kQuadThreads, kQuadThreads, 0, ts>>>(s->buckets.p, k * rper, b_hi, g.nbw, s->ranges.p);
+        PLK_LAUNCHED();
+        // chunk sums of this part's ranges down to <= 16 values, ping-pong in the two small buffers; every part does the
+        // same number of passes, so the last pass of all parts lands contiguously in one buffer
+        const char* in = static_cast<const char*>(s->ranges.p) + (size_t)k * rper * xyzz;
+        unsigned cnt = rper;
+        int pass = 0;
+        while (cnt > 16) {
+          const unsigned chunk = (cnt + 15) / 16 < 8 ? (cnt + 15) / 16 : 8;
+          const unsigned nout = (cnt + chunk - 1) / chunk;
+          char* dst = static_cast<char*>(s->chunks[pass & 1].p) + (size_t)k * nout * xyzz;
+          msm_sum_chunks_kernel<C><<<(4 * nout + kQuadThreads - 1) / kQuadThreads, kQuadThreads, 0, ts>>>(in, cnt, chunk, dst);
+          PLK_LAUNCHED();
+          in = dst;
+          cnt = nout;
+          ++pass;
+        }
+        out_per = cnt;
+        last = pass ? s->chunks[(pass - 1) & 1].p : s->ranges.p;
+        if (trace) cudaEventRecord(tr_tail[k], ts);
+      }
+      if (trace) {
+        cudaStreamSynchronize(s->tail_st);
+        for (int k = 0; k < parts; ++k) {
+          float a = 0, b = 0;
+          cudaEventElapsedTime(&a, tr0, tr_acc[k]);
+          cudaEventElapsedTime(&b, tr0, tr_tail[k]);
+          fprintf(stderr, "[trace] part %d: accumulate done at %.3f ms, tail done at %.3f ms\n", k, a, b);
+        }
+      }
+      PLK_CUDA(cudaEventRecord(s->tail_ev, s->tail_st));
+      PLK_CUDA(cudaStreamWaitEvent(st, s->tail_ev, 0));
+      const unsigned fcount = out_per * parts;
+      unsigned fquads = 1;
+      while (fquads < fcount && fquads < 64) fquads <<= 1;
+      msm_final_kernel<C><<<1, 4 * fquads, fquads * xyzz, st>>>(last, fcount, d_partial, reinterpret_cast<uint32_t*>(d_out_xyz),
+                                                              reinterpret_cast<unsigned char*>(d_out_zero));
+      PLK_LAUNCHED();
+      return;
+    }
+    accumulate(st, 0, g.nb, ablocks);
   }
   s->timer.mark(st);
-  msm_bucket_sum_kernel<C><<<(2 * g.nb + 127) / 128, 128, 0, st>>>(s->partials.p, s->task_off.as<unsigned>(), g.nb, s->buckets.p,
+  msm_bucket_sum_kernel<C><<<(2 * g.nb + 127) / 128, 128, 0, st>>>(s->partials.p, s->task_off.as<unsigned>(), 0, g.nb, s->buckets.p,
                                                                s->big_list.as<unsigned>());
   PLK_LAUNCHED();
   msm_big_bucket_kernel<C><<<64, 256, 256 * xyzz, st>>>(s->partials.p, s->task_off.as<unsigned>(), s->buckets.p, s->big_list.as<unsigned>());
   PLK_LAUNCHED();
   s->timer.mark(st);
   const unsigned nranges = (g.nb + kRangeSize - 1) / kRangeSize;
-  msm_range_kernel<C><<<(4 * nranges + kQuadThreads - 1) / kQuadThreads, kQuadThreads, 0, st>>>(s->buckets.p, g.nb, g.nbw, s->ranges.p);
+  msm_range_kernel<C><<<(4 * nranges + kQuadThreads - 1) / kQuadThreads, kQuadThreads, 0, st>>>(s->buckets.p, 0, g.nb, g.nbw, s->ranges.p);
   PLK_LAUNCHED();
   s->timer.mark(st);
   const void* fin = s->ranges.p;

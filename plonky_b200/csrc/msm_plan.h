@@ -13,6 +13,7 @@ constexpr int kMaddCompactDefault = 1;   // accumulate kernel: 0 fully inlined m
 constexpr int kQuadThreads = 64;     // CTA size of the quad-cooperative tail kernels (16 quads)
 constexpr int kFinalQuadsMax = 64;   // quads of the single-CTA final reduction
 constexpr int kAffineRoundsHostMax = 3;  // = kAffineRoundsMax of msm_affine.cuh
+constexpr int kPartsMax = 8;         // bucket ranges of the overlapped pipeline (execute_one)
 constexpr unsigned kSortMaxBins = 32768;   // shared-memory histogram sort: nb * 4 B <= 128 KiB
 
 struct MsmGeom {
@@ -39,6 +40,51 @@ struct plk_msm_scratch {
   int affine_rounds = 0;   // 0 = XYZZ accumulation straight from the table
   unsigned sort_rows = 0;  // CTAs of the shared-memory sort; 0 = global-atomic counting sort
   plk::PhaseTimer timer;   // count | scan | scatter | accumulate | bucket_sum | range | final
+  // overlapped pipeline (execute_one): streams of the accumulate parts 1.., the high-priority stream of the reduction
+  // tails, their events, and two small ping-pong buffers for the per-part chunk sums
+  plk::DevBuf chunks[2];
+  cudaStream_t part_st[plk::kPartsMax] = {}, tail_st = nullptr;
+  cudaEvent_t fork_ev = nullptr, tail_ev = nullptr, acc_ev[plk::kPartsMax] = {};
+  int streams_made = 0;
+
+  // Number of bucket ranges this execute is cut into; 1 = the serial pipeline, which is the default: measured on B200
+  // the overlapped pipeline LOSES (2^20 terms: 3.19 ms serial, 3.27 / 3.59 / 4.33 ms with 2 / 4 / 8 parts) --
+  // a tail running under the next part's accumulation shares each scheduler with twelve accumulate warps and its
+  // dependent chain stretches from 0.3 to 1.3 ms.  PLK_MSM_OVERLAP_PARTS = 2 | 4 | 8 switches it on (tests, profiles).
+  // Always serial while phase timings are taken, and for variable-base and batched-affine geometries.
+  int parts_for(const plk::MsmGeom& g, bool temporary) const {
+    if (g.variable || g.affine_rounds > 0 || temporary || plk::g_profiling.load(std::memory_order_relaxed)) return 1;
+    static const int want = getenv("PLK_MSM_OVERLAP_PARTS") ? atoi(getenv("PLK_MSM_OVERLAP_PARTS")) : 1;
+    int p = 1;
+    while (2 * p <= want && 2 * p <= plk::kPartsMax && g.nb / (2 * p) >= 8u * plk::kRangeSize) p *= 2;
+    return p;
+  }
+  void ensure_streams(int parts) {
+    if (!fork_ev) {
+      int least = 0, greatest = 0;
+      PLK_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+      PLK_CUDA(cudaStreamCreateWithPriority(&tail_st, cudaStreamNonBlocking, greatest));
+      PLK_CUDA(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
+      PLK_CUDA(cudaEventCreateWithFlags(&tail_ev, cudaEventDisableTiming));
+      for (auto& e : acc_ev) PLK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    // the parts must be accumulated IN ORDER for their tails to overlap anything: equal-priority streams are drained
+    // round-robin (all parts finish together, measured), so part k gets the k-th priority below the tail stream
+    for (; streams_made < parts; ++streams_made) {
+      int least = 0, greatest = 0;
+      PLK_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+      int prio = greatest + 1 + streams_made;
+      if (prio > least) prio = least;
+      PLK_CUDA(cudaStreamCreateWithPriority(&part_st[streams_made], cudaStreamNonBlocking, prio));
+    }
+  }
+  ~plk_msm_scratch() {
+    for (auto q : part_st) if (q) cudaStreamDestroy(q);
+    if (tail_st) cudaStreamDestroy(tail_st);
+    if (fork_ev) cudaEventDestroy(fork_ev);
+    if (tail_ev) cudaEventDestroy(tail_ev);
+    for (auto e : acc_ev) if (e) cudaEventDestroy(e);
+  }
 };
 
 struct plk_msm_table {

@@ -2,7 +2,8 @@
 re-runs the relevant parity tests in a child process with the knob set.
   PLK_NTT_TMA=1              every qualifying NTT pass through the TMA / Stockham kernel (csrc/ntt_tma.cuh)
   PLK_MSM_AFFINE_ROUNDS=2    batched-affine bucket rounds in front of the XYZZ accumulation (csrc/msm_affine.cuh)
-  PLK_MSM_MADD_COMPACT=0/2   the other two code-size variants of the mixed addition"""
+  PLK_MSM_MADD_COMPACT=0/2   the other two code-size variants of the mixed addition
+  PLK_MSM_OVERLAP_PARTS=2/8  the overlapped pipeline: bucket ranges accumulated on their own streams, reduction tails underneath"""
 import os
 import subprocess
 import sys
@@ -38,3 +39,8 @@ def test_msm_parity_with_batched_affine_rounds(rounds):
 @pytest.mark.parametrize("variant", ["0", "2"])
 def test_msm_parity_with_other_madd_variants(variant):
     run_child({"PLK_MSM_MADD_COMPACT": variant}, "msm", ["test_gpu_parity.py", "test_gpu_edge.py"])
+
+
+@pytest.mark.parametrize("parts,mode", [("2", "0"), ("8", "0"), ("4", "1")])
+def test_msm_parity_with_overlapped_pipeline(parts, mode):
+    run_child({"PLK_MSM_OVERLAP_PARTS": parts, "PLK_MSM_OVERLAP_MODE": mode}, "msm or shard or ipa", ["test_gpu_parity.py", "test_gpu_edge.py", "test_gpu_sharded.py"])

@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
 """Sweep of the MSM execute knobs on one GPU (tuning aid): PLK_MSM_AFFINE_ROUNDS x PLK_MSM_AFF_PER_THREAD x PLK_MSM_TASK.
+   PLK_MSM_OVERLAP_PARTS (read once per process) is swept from the shell: the printed point_crc must not change.
    python tools/tune_msm.py [--log-n 20] [--curve 0]"""
 import argparse, itertools, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -50,5 +51,6 @@ for w, r, per, task in itertools.product(args.window.split(","), args.rounds.spl
     if ref is None:
         ref = res
     ok = bool(np.array_equal(res, ref))
-    print(f"window={w} rounds={r} per={per} task={task}: {ms:.3f} ms  phases={' '.join(f'{x:.3f}' for x in ph)}  info={pk.msm_table_info(t)} same_point={ok}", flush=True)
+    print(f"window={w} rounds={r} per={per} task={task}: {ms:.3f} ms  phases={' '.join(f'{x:.3f}' for x in ph)}  info={pk.msm_table_info(t)} same_point={ok} "
+          f"overlap_parts={os.environ.get('PLK_MSM_OVERLAP_PARTS', 'auto')} point_crc={int(res.view(np.uint64).sum() & np.uint64(0xffffffff)):08x}", flush=True)
     t.close()
