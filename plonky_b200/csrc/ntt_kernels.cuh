@@ -152,13 +152,22 @@ struct TileGeom {
   unsigned long long k0;      // in-place: k'' of column 0 ; first: jlow of column 0
 };
 
-template <class F, int Q, bool LAYER0, bool FUSE_TW = false>
+// GEO = 1: the tile geometry is the compile-time constant (2^kGeoR rows, 2^kGeoLogT columns, kNttThreads threads) of every pass
+// of the headline sizes -- all index arithmetic of the load / store loops and the rounds folds into constants and
+// per-thread bases (the generic loops spend ~20 % of the kernel's instructions on 64-bit shifts, bit reversals and
+// swizzles per 16-byte piece).  GEO = 0: geometry read from the parameters.
+constexpr int kGeoR = 8, kGeoLogT = 3;
+
+template <class F, int Q, bool LAYER0, bool FUSE_TW = false, int GEO = 0>
 __device__ __forceinline__ void ntt_round(const NttPassParams& p, uint4* smem, const uint4* wsub, int l0, unsigned long long k0 = 0) {
-  const int T = 1 << p.log_t, elems = 1 << (p.r + p.log_t);
+  const int log_t = GEO ? kGeoLogT : p.log_t, pr = GEO ? kGeoR : p.r;
+  const int T = 1 << log_t, elems = 1 << (pr + log_t);
   const int groups = elems >> Q;
-  for (int gi = threadIdx.x; gi < groups; gi += blockDim.x) {
+  const int nthreads = GEO ? kNttThreads : (int)blockDim.x;
+#pragma unroll 1
+  for (int gi = threadIdx.x; gi < groups; gi += nthreads) {
     const int col = gi & (T - 1);
-    const int gr = gi >> p.log_t;
+    const int gr = gi >> log_t;
     const int low = gr & ((1 << l0) - 1);
     const int base_row = low | ((gr >> l0) << (l0 + Q));
     F x[1 << Q];
@@ -173,7 +182,7 @@ __device__ __forceinline__ void ntt_round(const NttPassParams& p, uint4* smem, c
       const size_t kk = (size_t)(k0 + col);
 #pragma unroll
       for (int e = 0; e < (1 << Q); ++e) {
-        const size_t orow = bitrev((unsigned)(base_row + e), p.r);
+        const size_t orow = bitrev((unsigned)(base_row + e), pr);
         if (p.tw_all || (orow != 0 && kk != 0)) x[e] = F::mul(x[e], load_fp<F>(p.tw_direct, (orow << p.log_m) + kk));
       }
     }
@@ -244,44 +253,47 @@ __device__ __noinline__ void ntt_post_factors(const NttPassParams& p, const Tile
 
 // MAXQ = 3: radix-8 register rounds, 2 CTAs per SM (128 registers).  MAXQ = 2: radix-4 rounds, 3 CTAs per SM
 // (85 registers): more shared-memory round trips, more warps to hide them behind.
-template <class F, int MAXQ>
+template <class F, int MAXQ, int GEO = 0>
 __global__ void __launch_bounds__(kNttThreads, MAXQ == 3 ? 2 : 3) ntt_pass_kernel(NttPassParams p) {
   extern __shared__ uint4 smem[];
   constexpr int PIECES = F::N / 4;
-  const int T = 1 << p.log_t, R = 1 << p.r, elems = R * T;
+  const int log_t = GEO ? kGeoLogT : p.log_t, pr = GEO ? kGeoR : p.r;
+  const int nthreads = GEO ? kNttThreads : (int)blockDim.x;
+  const int T = 1 << log_t, R = 1 << pr, elems = R * T;
   const unsigned long long tile = blockIdx.x;
   const uint4* in = reinterpret_cast<const uint4*>(p.in) + (size_t)blockIdx.y * p.in_stride * PIECES;
   uint4* out = reinterpret_cast<uint4*>(p.out);   // batch row offset is applied by ntt_out_index
 
   TileGeom g;
   if (p.first) {
-    g.k0 = tile << p.log_t;             // jlow of column 0
+    g.k0 = tile << log_t;               // jlow of column 0
     g.gbase = g.k0;
-    g.rowshift = p.log_n - p.r;         // input stride of j_m
+    g.rowshift = p.log_n - pr;          // input stride of j_m
   } else {
-    const int tph = p.log_m - p.log_t;  // log2 tiles per hi block
+    const int tph = p.log_m - log_t;    // log2 tiles per hi block
     const unsigned long long hi = tile >> tph;
-    g.k0 = (tile & ((1ull << tph) - 1)) << p.log_t;
-    g.gbase = g.k0 + (hi << (p.log_m + p.r));
+    g.k0 = (tile & ((1ull << tph) - 1)) << log_t;
+    g.gbase = g.k0 + (hi << (p.log_m + pr));
     g.rowshift = p.log_m;
   }
 
   // the 128 sub-transform twiddles live in shared memory behind the tile (fixed 29-cycle LDS instead of
   // L1/L2 round trips on the butterflies' critical path)
   uint4* wsub_s = smem + (size_t)PIECES * elems;
-  for (int idx = threadIdx.x; idx < (1 << (kSubLog - 1)) * PIECES; idx += blockDim.x)
+  for (int idx = threadIdx.x; idx < (1 << (kSubLog - 1)) * PIECES; idx += nthreads)
     wsub_s[idx] = reinterpret_cast<const uint4*>(p.wsub)[idx];
 
   // ---- load: 16-byte pieces, columns fastest (256 B contiguous per row), global -> shared directly with
   // cp.async (LDGSTS): all of a thread's 16 pieces are in flight at once and no register staging is
   // needed; rows at or beyond n_in (zero padding of the LDE) are zero-filled without touching memory.
-  for (int idx = threadIdx.x; idx < elems * PIECES; idx += blockDim.x) {
+#pragma unroll(GEO ? 16 : 1)
+  for (int idx = threadIdx.x; idx < elems * PIECES; idx += nthreads) {
     const int piece = idx % PIECES;
     const int e = idx / PIECES;
     const int col = e & (T - 1);
-    const int row = e >> p.log_t;
+    const int row = e >> log_t;
     const unsigned long long gidx = g.gbase + col + ((unsigned long long)row << g.rowshift);
-    const int srow = (int)bitrev((unsigned)row, p.r);
+    const int srow = (int)bitrev((unsigned)row, pr);
     uint4* dst = &smem[piece * elems + srow * T + (col ^ (srow & (T - 1)))];
     const bool present = !p.first || gidx < p.n_in;
     const uint4* src = in + (present ? gidx * PIECES + piece : 0);
@@ -294,11 +306,18 @@ __global__ void __launch_bounds__(kNttThreads, MAXQ == 3 ? 2 : 3) ntt_pass_kerne
   __syncthreads();
 
   // ---- input-side factors, then butterflies as radix-8 / 4 / 2 register rounds ----
-  const bool fuse_tw = MAXQ == 2 && !p.first && !p.tw_none && !p.scale && p.tw_direct && p.r >= 2;
+  const bool fuse_tw = MAXQ == 2 && !p.first && !p.tw_none && !p.scale && p.tw_direct && pr >= 2;
   if (!fuse_tw && ((p.first && p.pre_lo) || (!p.first && !p.tw_none) || p.scale)) ntt_pre_factors<F>(p, g, smem);
   {
     int l0 = 0;
-    const int r = p.r;
+    const int r = pr;
+    if (GEO) {
+      // kGeoR = 8 rows bits, radix-4 rounds only (the host selects GEO = 1 for MAXQ == 2)
+      if (fuse_tw) ntt_round<F, 2, true, true, GEO>(p, smem, wsub_s, 0, g.k0);
+      else ntt_round<F, 2, true, false, GEO>(p, smem, wsub_s, 0);
+#pragma unroll 1
+      for (l0 = 2; l0 < kGeoR; l0 += 2) ntt_round<F, 2, false, false, GEO>(p, smem, wsub_s, l0);
+    } else {
     if (MAXQ >= 3 && r >= 3) { ntt_round<F, (MAXQ >= 3 ? 3 : 2), true>(p, smem, wsub_s, 0); l0 = 3; }
     else if (r >= 2) {
       if (fuse_tw) ntt_round<F, 2, true, true>(p, smem, wsub_s, 0, g.k0);
@@ -313,16 +332,18 @@ __global__ void __launch_bounds__(kNttThreads, MAXQ == 3 ? 2 : 3) ntt_pass_kerne
       else ntt_round<F, 1, false>(p, smem, wsub_s, l0);
       l0 += q;
     }
+    }
   }
   if (p.last && (p.post_lo || p.post_periodic)) ntt_post_factors<F>(p, g, smem);
 
   // ---- store ----
   if (!p.first) {
-    for (int idx = threadIdx.x; idx < elems * PIECES; idx += blockDim.x) {
+#pragma unroll(GEO ? 16 : 1)
+    for (int idx = threadIdx.x; idx < elems * PIECES; idx += nthreads) {
       const int piece = idx % PIECES;
       const int e = idx / PIECES;
       const int col = e & (T - 1);
-      const int row = e >> p.log_t;
+      const int row = e >> log_t;
       const unsigned long long gidx = g.gbase + col + ((unsigned long long)row << g.rowshift);
       uint4* dst = p.last ? ntt_out_ptr(p, out, gidx, blockIdx.y, PIECES)
                           : out + ((unsigned long long)blockIdx.y * p.out_stride + gidx) * PIECES;
@@ -330,17 +351,18 @@ __global__ void __launch_bounds__(kNttThreads, MAXQ == 3 ? 2 : 3) ntt_pass_kerne
     }
   } else {
     // column c of the tile becomes a run of R contiguous outputs at rev_digits(jlow) * R
-    for (int idx = threadIdx.x; idx < elems * PIECES; idx += blockDim.x) {
+#pragma unroll(GEO ? 4 : 1)
+    for (int idx = threadIdx.x; idx < elems * PIECES; idx += nthreads) {
       const int piece = idx % PIECES;
       const int e = idx / PIECES;
       const int row = e & (R - 1);
-      const int col = e >> p.r;
+      const int col = e >> pr;
       unsigned long long x = g.k0 + col, pos = 0;
       for (int i = 0; i < p.ndig; ++i) {
         pos = (pos << p.digs[i]) | (x & ((1ull << p.digs[i]) - 1));
         x >>= p.digs[i];
       }
-      const unsigned long long gidx = (pos << p.r) + row;
+      const unsigned long long gidx = (pos << pr) + row;
       uint4* dst = p.last ? ntt_out_ptr(p, out, gidx, blockIdx.y, PIECES)
                           : out + ((unsigned long long)blockIdx.y * p.out_stride + gidx) * PIECES;
       dst[piece] = smem[piece * elems + row * T + (col ^ (row & (T - 1)))];
