@@ -38,6 +38,17 @@ namespace plk {
 #ifdef __CUDACC__
 static __constant__ uint32_t kMontMu32 = 0xffffffffu;
 #endif
+// Two measured alternatives for the reduction rows, both off (tools/bench_mul.cu on B200, products/s, Tweedle | 377-bit):
+//   baseline 7.34e10 | 2.96e10;  PLK_MOD_LIMB_ONE_AS_ADD (modulus limb 0 == 1 as two additions instead of IMAD + IMAD.HI)
+//   7.39e10 | 3.05e10, squarings 8.33 -> 8.23e10;  + PLK_MU_AS_NEG (quotient digit as an opaque negation) 7.36e10 | 3.08e10.
+// ptxas re-balances by itself: the additions it is handed come back as IMAD.X / IMAD.MOV on the FMA pipe (16 -> 14 narrow
+// IMADs per product instead of 16 -> 0), so the gain stays inside the noise for the 8-limb fields.
+#ifndef PLK_MU_AS_NEG
+#define PLK_MU_AS_NEG 0
+#endif
+#ifndef PLK_MOD_LIMB_ONE_AS_ADD
+#define PLK_MOD_LIMB_ONE_AS_ADD 0
+#endif
 namespace ptx {
 #ifdef __CUDA_ARCH__
 PLK_HD uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
@@ -178,7 +189,11 @@ struct Fp {
 #pragma unroll
     for (int j = 0; j < N; j += 2) {
       const bool last = !(j + 2 < N || COUT);
-      if (P::mod(start + j) != 0) {
+      if (PLK_MOD_LIMB_ONE_AS_ADD && P::mod(start + j) == 1) {
+        // limb == 1: the 64-bit product is just y -- two additions on the ALU pipe instead of an IMAD / IMAD.HI pair
+        acc[j] = (j == 0) ? ptx::add_cc(acc[j], y) : ptx::addc_cc(acc[j], y);
+        acc[j + 1] = last ? ptx::addc(acc[j + 1], 0) : ptx::addc_cc(acc[j + 1], 0);
+      } else if (P::mod(start + j) != 0) {
         acc[j] = (j == 0) ? ptx::mad_lo_cc(P::mod(start + j), y, acc[j]) : ptx::madc_lo_cc(P::mod(start + j), y, acc[j]);
         acc[j + 1] = last ? ptx::madc_hi(P::mod(start + j), y, acc[j + 1]) : ptx::madc_hi_cc(P::mod(start + j), y, acc[j + 1]);
       } else {
@@ -213,7 +228,10 @@ struct Fp {
       }
       mad_chain<false, true, N + 1>(E, a.l, 0, b.l[i]);
       static_assert(P::MU32 == 0xffffffffu, "kMontMu32 assumes p == 1 mod 2^32");
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && PLK_MU_AS_NEG
+      uint32_t m;
+      asm volatile("sub.u32 %0, 0, %1;" : "=r"(m) : "r"(E[0]));
+#elif defined(__CUDA_ARCH__)
       uint32_t m = E[0] * kMontMu32;        // quotient digit
 #else
       uint32_t m = E[0] * P::MU32;

@@ -152,15 +152,15 @@ struct TileGeom {
   unsigned long long k0;      // in-place: k'' of column 0 ; first: jlow of column 0
 };
 
-// GEO = 1: the tile geometry is the compile-time constant (2^kGeoR rows, 2^kGeoLogT columns, kNttThreads threads) of every pass
-// of the headline sizes -- all index arithmetic of the load / store loops and the rounds folds into constants and
-// per-thread bases (the generic loops spend ~20 % of the kernel's instructions on 64-bit shifts, bit reversals and
-// swizzles per 16-byte piece).  GEO = 0: geometry read from the parameters.
-constexpr int kGeoR = 8, kGeoLogT = 3;
+// GEO = r > 0: the tile geometry is a compile-time constant (2^GEO rows, 2^kGeoLogT columns, kNttThreads threads; GEO = 6, 7, 8
+// are instantiated: every pass of transforms of 2^16 points and more) -- all index arithmetic of the load / store loops
+// and the rounds folds into constants and per-thread bases (the generic loops spend ~20 % of the kernel's instructions
+// on 64-bit shifts, bit reversals and swizzles per 16-byte piece).  GEO = 0: geometry read from the parameters.
+constexpr int kGeoLogT = 3, kGeoRMin = 6, kGeoRMax = 8;
 
 template <class F, int Q, bool LAYER0, bool FUSE_TW = false, int GEO = 0>
 __device__ __forceinline__ void ntt_round(const NttPassParams& p, uint4* smem, const uint4* wsub, int l0, unsigned long long k0 = 0) {
-  const int log_t = GEO ? kGeoLogT : p.log_t, pr = GEO ? kGeoR : p.r;
+  const int log_t = GEO ? kGeoLogT : p.log_t, pr = GEO ? GEO : p.r;
   const int T = 1 << log_t, elems = 1 << (pr + log_t);
   const int groups = elems >> Q;
   const int nthreads = GEO ? kNttThreads : (int)blockDim.x;
@@ -257,9 +257,10 @@ template <class F, int MAXQ, int GEO = 0>
 __global__ void __launch_bounds__(kNttThreads, MAXQ == 3 ? 2 : 3) ntt_pass_kernel(NttPassParams p) {
   extern __shared__ uint4 smem[];
   constexpr int PIECES = F::N / 4;
-  const int log_t = GEO ? kGeoLogT : p.log_t, pr = GEO ? kGeoR : p.r;
+  const int log_t = GEO ? kGeoLogT : p.log_t, pr = GEO ? GEO : p.r;
   const int nthreads = GEO ? kNttThreads : (int)blockDim.x;
   const int T = 1 << log_t, R = 1 << pr, elems = R * T;
+  constexpr int kPieceIters = GEO ? ((1 << (GEO + kGeoLogT)) * PIECES) / kNttThreads : 1;   // trip count of the piece loops
   const unsigned long long tile = blockIdx.x;
   const uint4* in = reinterpret_cast<const uint4*>(p.in) + (size_t)blockIdx.y * p.in_stride * PIECES;
   uint4* out = reinterpret_cast<uint4*>(p.out);   // batch row offset is applied by ntt_out_index
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(kNttThreads, MAXQ == 3 ? 2 : 3) ntt_pass_kerne
   // ---- load: 16-byte pieces, columns fastest (256 B contiguous per row), global -> shared directly with
   // cp.async (LDGSTS): all of a thread's 16 pieces are in flight at once and no register staging is
   // needed; rows at or beyond n_in (zero padding of the LDE) are zero-filled without touching memory.
-#pragma unroll(GEO ? 16 : 1)
+#pragma unroll(kPieceIters)
   for (int idx = threadIdx.x; idx < elems * PIECES; idx += nthreads) {
     const int piece = idx % PIECES;
     const int e = idx / PIECES;
@@ -312,11 +313,12 @@ __global__ void __launch_bounds__(kNttThreads, MAXQ == 3 ? 2 : 3) ntt_pass_kerne
     int l0 = 0;
     const int r = pr;
     if (GEO) {
-      // kGeoR = 8 rows bits, radix-4 rounds only (the host selects GEO = 1 for MAXQ == 2)
+      // radix-4 rounds, one radix-2 round at the end when GEO is odd (the host selects GEO > 0 for MAXQ == 2 only)
       if (fuse_tw) ntt_round<F, 2, true, true, GEO>(p, smem, wsub_s, 0, g.k0);
       else ntt_round<F, 2, true, false, GEO>(p, smem, wsub_s, 0);
 #pragma unroll 1
-      for (l0 = 2; l0 < kGeoR; l0 += 2) ntt_round<F, 2, false, false, GEO>(p, smem, wsub_s, l0);
+      for (l0 = 2; l0 + 2 <= GEO; l0 += 2) ntt_round<F, 2, false, false, GEO>(p, smem, wsub_s, l0);
+      if (GEO & 1) ntt_round<F, 1, false, false, GEO>(p, smem, wsub_s, GEO - 1);
     } else {
     if (MAXQ >= 3 && r >= 3) { ntt_round<F, (MAXQ >= 3 ? 3 : 2), true>(p, smem, wsub_s, 0); l0 = 3; }
     else if (r >= 2) {
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(kNttThreads, MAXQ == 3 ? 2 : 3) ntt_pass_kerne
 
   // ---- store ----
   if (!p.first) {
-#pragma unroll(GEO ? 16 : 1)
+#pragma unroll(kPieceIters)
     for (int idx = threadIdx.x; idx < elems * PIECES; idx += nthreads) {
       const int piece = idx % PIECES;
       const int e = idx / PIECES;
@@ -351,7 +353,7 @@ __global__ void __launch_bounds__(kNttThreads, MAXQ == 3 ? 2 : 3) ntt_pass_kerne
     }
   } else {
     // column c of the tile becomes a run of R contiguous outputs at rev_digits(jlow) * R
-#pragma unroll(GEO ? 4 : 1)
+#pragma unroll(kPieceIters < 4 ? kPieceIters : 4)
     for (int idx = threadIdx.x; idx < elems * PIECES; idx += nthreads) {
       const int piece = idx % PIECES;
       const int e = idx / PIECES;
