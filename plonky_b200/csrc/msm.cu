@@ -62,17 +62,38 @@ int pick_window_variable(size_t n) {
   return c;
 }
 
-// scratch of the stream `st` (created on first use)
-plk_msm_scratch* scratch_for(plk_msm_table* t, cudaStream_t st) {
+// accumulate task size for `entries` sorted entries spread over `nb` buckets: aim at >= ~75 K accumulate threads (4 CTAs of
+// 128 on each of the 148 SMs) so that small MSMs still fill the machine; large ones use the full 32-entry tasks
+unsigned pick_task(unsigned long long entries, unsigned nb) {
+  unsigned s = kTaskSizeMax;
+  while (s > 8 && entries / s < 75000) s >>= 1;
+  // very long buckets (2^21+ terms on one GPU): keep the task partials per bucket near 16, otherwise every bucket
+  // overflows into the one-CTA-per-bucket reduction (measured: BLS12-377 2^22 on one GPU, bucket_sum 50 ms)
+  while ((entries / (nb ? nb : 1)) / s > 16 && s < 1024) s <<= 1;
+  if (const char* e = getenv("PLK_MSM_TASK")) { int v = atoi(e); if (v >= 1 && v <= 1024) s = (unsigned)v; }
+  return s;
+}
+
+// scratch of the stream `st` for executes of `batch` merged vectors (created on first use)
+plk_msm_scratch* scratch_for(plk_msm_table* t, cudaStream_t st, unsigned batch = 1) {
   std::lock_guard<std::mutex> lk(t->mu);
-  auto it = t->scratch.find(st);
+  auto it = t->scratch.find(std::make_pair(st, batch));
   if (it == t->scratch.end()) {
-    const MsmGeom& g = t->g;
+    MsmGeom g = t->g;
+    if (batch > 1) {
+      g.batch = batch;
+      g.n_pts = t->g.n;
+      g.n = t->g.n * batch;
+      g.nb = t->g.nbw * batch;
+      g.task = pick_task(g.n * (unsigned long long)g.nwin, g.nb);
+    }
     const size_t entries = (size_t)g.n * g.nwin;
-    t->max_tasks = ((entries >> g.affine_rounds) + g.nb) / g.task + g.nb + 1;
+    const size_t max_tasks = ((entries >> g.affine_rounds) + g.nb) / g.task + g.nb + 1;
     const size_t xyzz = 2 * t->point_bytes;
     auto* s = new plk_msm_scratch();
     s->affine_rounds = g.affine_rounds;
+    s->g = g;
+    s->max_tasks = max_tasks;
     if (t->temporary)
       for (plk::DevBuf* b : {&s->counts, &s->offsets, &s->task_off, &s->cursors, &s->sorted, &s->partials, &s->buckets, &s->ranges, &s->big_list,
                              &s->cta_hist, &s->chunks[0], &s->chunks[1]})
@@ -83,7 +104,7 @@ plk_msm_scratch* scratch_for(plk_msm_table* t, cudaStream_t st) {
       s->task_off.alloc(((size_t)g.nb + 1) * 4);
       s->cursors.alloc((size_t)g.nb * 4);
       s->sorted.alloc((entries ? entries : 1) * 4);
-      s->partials.alloc(t->max_tasks * xyzz);
+      s->partials.alloc(max_tasks * xyzz);
       s->buckets.alloc((size_t)g.nb * xyzz);
       s->ranges.alloc(((size_t)g.nb / kRangeSize + 1) * xyzz);
       s->big_list.alloc(((size_t)g.nb + 1 + plk::kPartsMax) * 4);        // one list (count + entries) per part of the overlapped pipeline
@@ -113,7 +134,7 @@ plk_msm_scratch* scratch_for(plk_msm_table* t, cudaStream_t st) {
       delete s;
       throw;
     }
-    it = t->scratch.emplace(st, s).first;
+    it = t->scratch.emplace(std::make_pair(st, batch), s).first;
   }
   t->last = it->second;
   return it->second;
@@ -121,6 +142,22 @@ plk_msm_scratch* scratch_for(plk_msm_table* t, cudaStream_t st) {
 void alloc_scratch(plk_msm_table* t) {
   const MsmGeom& g = t->g;
   t->max_tasks = ((((size_t)g.n * g.nwin) >> g.affine_rounds) + g.nb) / g.task + g.nb + 1;
+}
+// Merged batches (opt-in): up to kMergeMax vectors of a short MSM run as one pipeline with one bucket set per
+// vector -- the sort, the accumulation and the reduction tails are each ONE launch over all vectors.  Measured on B200,
+// 9 vectors of 2^16 terms: 2.74 ms merged against 2.61 ms for the default fork/join over 8 side streams (16 x 2^12:
+// 1.34 vs 1.33 ms); the accumulation floor is 1.5 ms either way, and the merged bucket set (9 x 2^14 buckets) no longer
+// fits the shared-memory sort.  PLK_MSM_BATCH_MERGE = m (2..16) enables it with at most m vectors per merged execute.
+constexpr size_t kMergeMax = 16;
+size_t merge_width(const plk_msm_table* t, size_t k) {
+  static const int env = getenv("PLK_MSM_BATCH_MERGE") ? atoi(getenv("PLK_MSM_BATCH_MERGE")) : 0;
+  const MsmGeom& g = t->g;
+  if (env <= 1 || k < 2 || g.variable || g.affine_rounds > 0 || t->temporary || g.n == 0) return 1;
+  if (g.n * (unsigned long long)g.nwin > (1ull << 22)) return 1;          // long MSMs already fill the machine on their own
+  size_t m = k < (size_t)env ? k : (size_t)env;
+  if (m > kMergeMax) m = kMergeMax;
+  while (m > 1 && ((unsigned long long)g.nbw * m > (1u << 22) || g.n * (unsigned long long)g.nwin * m >= (1ull << 31))) --m;
+  return m;
 }
 void run_one(plk_msm_table* t, const void* d_scalars, void* d_out_xyz, void* d_out_zero, void* d_partial, cudaStream_t st) {
   ops_for(t->curve)->execute_one(t, scratch_for(t, st), d_scalars, d_out_xyz, d_out_zero, d_partial, st);
@@ -138,6 +175,18 @@ void run_batch(plk_msm_table* t, const char* d_scalars, size_t k, char* d_out_xy
     return;
   }
   std::lock_guard<std::mutex> batch_lock(t->batch_mu);
+  const size_t width = merge_width(t, k);
+  if (width > 1) {
+    // merged executes of `width` vectors each, back to back on the caller's stream (each one fills the machine)
+    if (h_scalars && sbytes) PLK_CUDA(cudaMemcpyAsync(const_cast<char*>(d_scalars), h_scalars, k * sbytes, cudaMemcpyHostToDevice, st));
+    for (size_t j = 0; j < k; j += width) {
+      const size_t m = k - j < width ? k - j : width;
+      if (m == 1) { run_one(t, d_scalars + j * sbytes, d_out_xyz + j * 3 * L * 8, d_out_zero + j, nullptr, st); continue; }
+      ops_for(t->curve)->execute_one(t, scratch_for(t, st, (unsigned)m), d_scalars + j * sbytes, d_out_xyz + j * 3 * L * 8, d_out_zero + j,
+                                     nullptr, st);
+    }
+    return;
+  }
   {
     std::lock_guard<std::mutex> lk(t->mu);
     if (!t->fork_ev) {
@@ -192,14 +241,9 @@ plk_msm_table* new_table(int curve, size_t n, unsigned w, bool variable = false)
     int rounds = 0;
     if (const char* e = getenv("PLK_MSM_AFFINE_ROUNDS")) { int v = atoi(e); if (v >= 0 && v <= kAffineRoundsHostMax && !variable) rounds = v; }
     t->g.affine_rounds = rounds;
-    const unsigned long long left = entries >> rounds;          // entries the XYZZ stage still sees
-    unsigned s = kTaskSizeMax;
-    while (s > 8 && left / s < 75000) s >>= 1;
-    // very long buckets (2^21+ terms on one GPU): keep the task partials per bucket near 16, otherwise every bucket
-    // overflows into the one-CTA-per-bucket reduction (measured: BLS12-377 2^22 on one GPU, bucket_sum 50 ms)
-    while ((left / (t->g.nb ? t->g.nb : 1)) / s > 16 && s < 1024) s <<= 1;
-    if (const char* e = getenv("PLK_MSM_TASK")) { int v = atoi(e); if (v >= 1 && v <= 1024) s = (unsigned)v; }
-    t->g.task = s;
+    t->g.task = pick_task(entries >> rounds, t->g.nb);           // entries the XYZZ stage still sees
+    t->g.batch = 1;
+    t->g.n_pts = n;
   }
   if ((unsigned long long)n * t->g.nwin >= (1ull << 31)) { delete t; fail(PLK_EINVAL, "too many terms for 31-bit table slots"); }
   return t;

@@ -33,8 +33,9 @@
 namespace plk {
 
 // signed window recoding of a canonical scalar; calls f(window, bucket_index, negative)
+// `base`: first bucket of the vector's bucket set (merged batch), 0 otherwise
 template <class SF, class Fn>
-__device__ __forceinline__ void for_each_digit(const SF& canon, const MsmGeom& g, Fn&& f) {
+__device__ __forceinline__ void for_each_digit(const SF& canon, const MsmGeom& g, unsigned base, Fn&& f) {
   if (g.c == 16 && !g.variable && g.nwin <= 2 * SF::N) {
     // 16-bit windows are the two halves of each limb: fully unrolled, no dynamic limb indexing (the generic loop
     // below costs ~1500 instructions per scalar, most of them address arithmetic around canon.l[limb])
@@ -46,9 +47,9 @@ __device__ __forceinline__ void for_each_digit(const SF& canon, const MsmGeom& g
         carry = 0;
         if (raw > 0x8000u) {
           carry = 1;
-          if (raw != 0x10000u) f(j, 0x10000u - raw - 1, true);
+          if (raw != 0x10000u) f(j, base + (0x10000u - raw - 1), true);
         } else if (raw != 0) {
-          f(j, raw - 1, false);
+          f(j, base + (raw - 1), false);
         }
       }
     }
@@ -67,10 +68,21 @@ __device__ __forceinline__ void for_each_digit(const SF& canon, const MsmGeom& g
     if (raw > halfw) {
       // digit = raw - 2^c (negative or, when raw == 2^c, zero), carry one into the next window
       carry = 1;
-      if (raw != full) f(j, (g.variable ? (unsigned)j * g.nbw : 0u) + (full - raw - 1), true);
+      if (raw != full) f(j, base + (g.variable ? (unsigned)j * g.nbw : 0u) + (full - raw - 1), true);
     } else if (raw != 0) {
-      f(j, (g.variable ? (unsigned)j * g.nbw : 0u) + (raw - 1), false);
+      f(j, base + (g.variable ? (unsigned)j * g.nbw : 0u) + (raw - 1), false);
     }
+  }
+}
+
+// term i of a (possibly merged) execute: vector v = i / n_pts, point index i - v * n_pts, bucket set base v * nbw
+__device__ __forceinline__ void term_of(const MsmGeom& g, unsigned long long i, unsigned long long& idx, unsigned& base) {
+  idx = i;
+  base = 0;
+  if (g.batch > 1) {
+    const unsigned v = (unsigned)(i / g.n_pts);
+    idx = i - (unsigned long long)v * g.n_pts;
+    base = v * g.nbw;
   }
 }
 
@@ -80,7 +92,10 @@ __global__ void msm_count_kernel(const uint4* __restrict__ scalars, MsmGeom g, u
   unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
   if (i >= g.n) return;
   SF s = SF::to_canonical(load_fp<SF>(scalars, i));     // curve_msm.rs:164 to_canonical_u64_vec
-  for_each_digit(s, g, [&](int, unsigned b, bool) { atomicAdd(&counts[b], 1u); });
+  unsigned long long idx;
+  unsigned base;
+  term_of(g, i, idx, base);
+  for_each_digit(s, g, base, [&](int, unsigned b, bool) { atomicAdd(&counts[b], 1u); });
 }
 
 // single CTA: offsets[b] = exclusive sum of counts, task_off[b] = exclusive sum of ceil(count / S);
@@ -137,10 +152,13 @@ __global__ void msm_scatter_kernel(const uint4* __restrict__ scalars, MsmGeom g,
   unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
   if (i >= g.n) return;
   SF s = SF::to_canonical(load_fp<SF>(scalars, i));
-  for_each_digit(s, g, [&](int j, unsigned b, bool negative) {
+  unsigned long long idx;
+  unsigned base;
+  term_of(g, i, idx, base);
+  for_each_digit(s, g, base, [&](int j, unsigned b, bool negative) {
     unsigned pos = atomicAdd(&cursors[b], 1u);
-    // entry = table slot (window-major: j * n + i) with the sign in bit 31 (n * nwin < 2^31 checked on host)
-    sorted[pos] = (unsigned)(g.variable ? i : (unsigned long long)j * g.n + i) | (negative ? 0x80000000u : 0u);
+    // entry = table slot (window-major: j * n_pts + idx) with the sign in bit 31 (n_pts * nwin < 2^31 checked on host)
+    sorted[pos] = (unsigned)(g.variable ? i : (unsigned long long)j * g.n_pts + idx) | (negative ? 0x80000000u : 0u);
   });
 }
 
@@ -163,7 +181,10 @@ __global__ void __launch_bounds__(1024) msm_hist_kernel(const uint4* __restrict_
   if (hi > g.n) hi = g.n;
   for (unsigned long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     SF s = SF::to_canonical(load_fp<SF>(scalars, i));     // curve_msm.rs:164 to_canonical_u64_vec
-    for_each_digit(s, g, [&](int, unsigned b, bool) { atomicAdd(&sh_bins[b], 1u); });
+    unsigned long long idx;
+    unsigned base;
+    term_of(g, i, idx, base);
+    for_each_digit(s, g, base, [&](int, unsigned b, bool) { atomicAdd(&sh_bins[b], 1u); });
   }
   __syncthreads();
   unsigned* row = cta_hist + (size_t)blockIdx.x * g.nb;
@@ -201,9 +222,12 @@ __global__ void __launch_bounds__(1024) msm_scatter_smem_kernel(const uint4* __r
   if (hi > g.n) hi = g.n;
   for (unsigned long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     SF s = SF::to_canonical(load_fp<SF>(scalars, i));
-    for_each_digit(s, g, [&](int j, unsigned b, bool negative) {
+    unsigned long long idx;
+    unsigned base;
+    term_of(g, i, idx, base);
+    for_each_digit(s, g, base, [&](int j, unsigned b, bool negative) {
       const unsigned pos = atomicAdd(&sh_bins[b], 1u);
-      sorted[pos] = (unsigned)((unsigned long long)j * g.n + i) | (negative ? 0x80000000u : 0u);
+      sorted[pos] = (unsigned)((unsigned long long)j * g.n_pts + idx) | (negative ? 0x80000000u : 0u);
     });
   }
 }
@@ -386,8 +410,12 @@ __global__ void __launch_bounds__(4 * kFinalQuadsMax) msm_final_kernel(const voi
   typename Q::Ctx qc = Q::make_ctx(quad_sm);
   const unsigned q = threadIdx.x >> 2, nq = blockDim.x >> 2;
   const int ql = qc.ql;
+  // block b (merged batch: one block per vector) sums in[b * count .. (b + 1) * count) into the b-th output
+  const size_t first = (size_t)blockIdx.x * count;
+  if (out_xyzz) out_xyzz = static_cast<char*>(out_xyzz) + (size_t)blockIdx.x * 4 * sizeof(F);
+  if (out_xyz) { out_xyz += (size_t)blockIdx.x * 3 * F::N; out_zero += blockIdx.x; }
   XYZZ<C> acc = XYZZ<C>::identity();
-  for (unsigned i = q; i < count; i += nq) acc = Q::add(acc, load_xyzz<C>(in, i), qc);
+  for (unsigned i = q; i < count; i += nq) acc = Q::add(acc, load_xyzz<C>(in, first + i), qc);
   if (ql == 0) store_xyzz<C>(sm, q, acc);
   __syncthreads();
   for (unsigned d = nq >> 1; d > 0; d >>= 1) {
@@ -706,7 +734,7 @@ template <class C>
 void execute_one(plk_msm_table* t, plk_msm_scratch* s, const void* d_scalars, void* d_out_xyz, void* d_out_zero, void* d_partial,
                  cudaStream_t st) {
   typedef Fp<typename C::Base> F;
-  const MsmGeom g = t->g;
+  const MsmGeom g = s->g;                 // the table's geometry, or a merged batch of it (run_batch)
   const size_t xyzz = 4 * sizeof(F);
   if (g.n == 0) {
     // empty sum = identity (curve_msm.rs: y stays ProjectivePoint::ZERO)
@@ -760,7 +788,7 @@ void execute_one(plk_msm_table* t, plk_msm_scratch* s, const void* d_scalars, vo
     PLK_LAUNCHED();
     s->timer.mark(st);
   }
-  const unsigned ablocks = (unsigned)((t->max_tasks + kAccThreads - 1) / kAccThreads);
+  const unsigned ablocks = (unsigned)((s->max_tasks + kAccThreads - 1) / kAccThreads);
   if (g.affine_rounds > 0) {
     // batched-affine tree rounds (msm_affine.cuh), then the XYZZ task kernel over the shortened lists
     const size_t entries = (size_t)g.n * g.nwin;
@@ -921,6 +949,22 @@ void execute_one(plk_msm_table* t, plk_msm_scratch* s, const void* d_scalars, vo
     }
     msm_window_combine_kernel<C><<<1, 4, 0, st>>>(fin, g.nwin, g.c, d_partial, reinterpret_cast<uint32_t*>(d_out_xyz),
                                                   reinterpret_cast<unsigned char*>(d_out_zero));
+    PLK_LAUNCHED();
+    s->timer.mark(st);
+    return;
+  }
+  if (g.batch > 1) {
+    // merged batch: chunk sums inside every vector's bucket set (sizes are powers of two: chunks never straddle two
+    // sets) down to <= 64 values per vector, then one final block per vector
+    unsigned per_set = g.nbw / kRangeSize;
+    while (per_set > 64) {
+      chunk_pass(8);
+      per_set /= 8;
+    }
+    unsigned bq = 1;
+    while (bq < per_set && bq < 64) bq <<= 1;
+    msm_final_kernel<C><<<g.batch, 4 * bq, bq * xyzz, st>>>(fin, per_set, nullptr, reinterpret_cast<uint32_t*>(d_out_xyz),
+                                                          reinterpret_cast<unsigned char*>(d_out_zero));
     PLK_LAUNCHED();
     s->timer.mark(st);
     return;

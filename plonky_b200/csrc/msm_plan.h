@@ -25,6 +25,11 @@ struct MsmGeom {
   int variable;             // 1: no table of powers, buckets per window, windows combined with doublings (msm_parallel)
   unsigned task;            // S: entries per accumulate task (power of two, <= kTaskSizeMax)
   int affine_rounds;        // batched-affine tree rounds before the XYZZ task kernel (0 = none)
+  // merged batch (run_batch): `batch` scalar vectors of n_pts terms each against the same fixed-base table run as ONE
+  // pipeline -- n = batch * n_pts terms, vector v owns the bucket set [v * nbw, (v + 1) * nbw), nb = batch * nbw.
+  // batch == 1: n_pts == n.
+  unsigned batch;
+  unsigned long long n_pts;
 };
 
 }  // namespace plk
@@ -40,6 +45,8 @@ struct plk_msm_scratch {
   int affine_rounds = 0;   // 0 = XYZZ accumulation straight from the table
   unsigned sort_rows = 0;  // CTAs of the shared-memory sort; 0 = global-atomic counting sort
   plk::PhaseTimer timer;   // count | scan | scatter | accumulate | bucket_sum | range | final
+  plk::MsmGeom g;          // geometry this scratch was sized for: the table's, or a merged batch of it
+  size_t max_tasks = 0;    // upper bound of accumulate tasks under g
   // overlapped pipeline (execute_one): streams of the accumulate parts 1.., the high-priority stream of the reduction
   // tails, their events, and two small ping-pong buffers for the per-part chunk sums
   plk::DevBuf chunks[2];
@@ -53,7 +60,7 @@ struct plk_msm_scratch {
   // dependent chain stretches from 0.3 to 1.3 ms.  PLK_MSM_OVERLAP_PARTS = 2 | 4 | 8 switches it on (tests, profiles).
   // Always serial while phase timings are taken, and for variable-base and batched-affine geometries.
   int parts_for(const plk::MsmGeom& g, bool temporary) const {
-    if (g.variable || g.affine_rounds > 0 || temporary || plk::g_profiling.load(std::memory_order_relaxed)) return 1;
+    if (g.variable || g.affine_rounds > 0 || g.batch > 1 || temporary || plk::g_profiling.load(std::memory_order_relaxed)) return 1;
     static const int want = getenv("PLK_MSM_OVERLAP_PARTS") ? atoi(getenv("PLK_MSM_OVERLAP_PARTS")) : 1;
     int p = 1;
     while (2 * p <= want && 2 * p <= plk::kPartsMax && g.nb / (2 * p) >= 8u * plk::kRangeSize) p *= 2;
@@ -99,7 +106,7 @@ struct plk_msm_table {
   cudaStream_t temp_stream = nullptr;
   std::mutex mu;                // guards the pools below (not the execution)
   std::mutex batch_mu;          // serialises the fork/join enqueue of the batch entry points
-  std::map<cudaStream_t, plk_msm_scratch*> scratch;   // keyed by the executing stream
+  std::map<std::pair<cudaStream_t, unsigned>, plk_msm_scratch*> scratch;   // keyed by the executing stream and the merged-batch size
   plk_msm_scratch* last = nullptr;                     // scratch of the most recent execute (phase timings)
   static constexpr int kSideStreamsMax = 8;
   int side_streams = 8;                                       // PLK_MSM_SIDE_STREAMS (1..8), read when the pool is created; 8 vs 4: prover mix 7.6 -> 7.2 ms

@@ -3,6 +3,7 @@ re-runs the relevant parity tests in a child process with the knob set.
   PLK_NTT_TMA=1              every qualifying NTT pass through the TMA / Stockham kernel (csrc/ntt_tma.cuh)
   PLK_MSM_AFFINE_ROUNDS=2    batched-affine bucket rounds in front of the XYZZ accumulation (csrc/msm_affine.cuh)
   PLK_MSM_MADD_COMPACT=0/2   the other two code-size variants of the mixed addition
+  PLK_MSM_BATCH_MERGE=16     batches of short vectors as ONE merged pipeline with a bucket set per vector (default: fork/join)
   PLK_MSM_OVERLAP_PARTS=2/8  the overlapped pipeline: bucket ranges accumulated on their own streams, reduction tails underneath"""
 import os
 import subprocess
@@ -44,3 +45,8 @@ def test_msm_parity_with_other_madd_variants(variant):
 @pytest.mark.parametrize("parts,mode", [("2", "0"), ("8", "0"), ("4", "1")])
 def test_msm_parity_with_overlapped_pipeline(parts, mode):
     run_child({"PLK_MSM_OVERLAP_PARTS": parts, "PLK_MSM_OVERLAP_MODE": mode}, "msm or shard or ipa", ["test_gpu_parity.py", "test_gpu_edge.py", "test_gpu_sharded.py"])
+
+
+@pytest.mark.parametrize("width", ["16", "3"])
+def test_msm_batches_as_merged_pipeline(width):
+    run_child({"PLK_MSM_BATCH_MERGE": width}, "batch or commit or ipa", ["test_gpu_parity.py", "test_serde.py", "test_ipa.py"])

@@ -308,6 +308,29 @@ def test_msm_batch_dev_concurrent_streams():
         assert np.array_equal(out[i].cpu().numpy().view(np.uint64), want)
 
 
+@pytest.mark.parametrize("name,n,k", [("Tweedledee", 1000, 19), ("Tweedledum", 4097, 5), ("Bls12377", 300, 4), ("Tweedledee", 1 << 14, 9)])
+def test_msm_batch_merged_pipeline(name, n, k):
+    """Batches through run_batch (csrc/msm.cu): the default fork/join over side streams here, and -- re-run by
+    test_gpu_optin_paths.py with PLK_MSM_BATCH_MERGE -- the merged pipeline (up to 16 short vectors as ONE sort / accumulate /
+    reduce with a bucket set per vector; k = 19 is one merged execute of 16 and one of 3): every vector's point must equal its own msm_execute,
+    including an all-zero vector (identity flag), a vector of equal scalars (every term of a window in one bucket: the
+    big-bucket path inside one set) and a vector with a single non-zero scalar."""
+    c = po.CURVES[name]
+    xy = rp.gen_points(c.cid, 17, n)
+    pre = pk.msm_precompute_affine(c.cid, xy, 11)
+    rows = [rand_scalars(c.scalar, 900 + i, n) for i in range(k)]
+    rows[1] = [0] * n
+    rows[2] = [c.scalar.p - 2] * n
+    rows[3] = [0] * (n - 1) + [5]
+    out, oz = pk.msm_execute_batch(pre, np.stack([mont_array(c.scalar, r) for r in rows]))
+    assert bool(oz[1]) and not out[1].any()
+    for i in range(k):
+        single, sz = pk.msm_execute(pre, mont_array(c.scalar, rows[i]))
+        assert np.array_equal(single, out[i]) and sz == bool(oz[i]), i
+    # one vector against the big-int oracle as well (the single execute is itself checked elsewhere)
+    assert result_point(c, out[3], oz[3]) == c.mul(5, array_to_point(c, xy[n - 1], 0))
+
+
 def test_msm_skewed_scalars():
     """All scalars equal / tiny: every term lands in the same bucket (worst-case load balance) and
     repeated identical points force the doubling branch."""
