@@ -211,7 +211,7 @@ static __global__ void msm_colsum_kernel(unsigned* __restrict__ cta_hist, unsign
 template <class C>
 __global__ void __launch_bounds__(1024) msm_scatter_smem_kernel(const uint4* __restrict__ scalars, MsmGeom g, unsigned chunk,
                                                                 const unsigned* __restrict__ cta_hist, const unsigned* __restrict__ offsets,
-                                                                unsigned* __restrict__ sorted) {
+                                                                unsigned* __restrict__ sorted, unsigned b_lo, unsigned b_hi) {
   typedef Fp<typename C::Scalar> SF;
   extern __shared__ unsigned sh_bins[];
   const unsigned* row = cta_hist + (size_t)blockIdx.x * g.nb;
@@ -226,6 +226,7 @@ __global__ void __launch_bounds__(1024) msm_scatter_smem_kernel(const uint4* __r
     unsigned base;
     term_of(g, i, idx, base);
     for_each_digit(s, g, base, [&](int j, unsigned b, bool negative) {
+      if (b < b_lo || b >= b_hi) return;         // another pass of the range-partitioned scatter (see execute_one)
       const unsigned pos = atomicAdd(&sh_bins[b], 1u);
       sorted[pos] = (unsigned)((unsigned long long)j * g.n_pts + idx) | (negative ? 0x80000000u : 0u);
     });
@@ -771,9 +772,23 @@ void execute_one(plk_msm_table* t, plk_msm_scratch* s, const void* d_scalars, vo
     s->timer.mark(st);
     launch_scan(s, g, st);
     s->timer.mark(st);
-    msm_scatter_smem_kernel<C><<<rows, 1024, smem, st>>>(reinterpret_cast<const uint4*>(d_scalars), g, chunk, s->cta_hist.as<unsigned>(),
-                                                         s->offsets.as<unsigned>(), s->sorted.as<unsigned>());
-    PLK_LAUNCHED();
+    // The scatter writes 4-byte entries all over `sorted`.  While the array fits in L2 (67 MB at 2^20 terms) the partial
+    // sectors merge there; beyond it they are evicted half-filled and fetched again (BLS12-377 2^22 on one GPU, 268 MB:
+    // 2.1 ms for 4x the entries that take 0.17 ms).  Then the scatter runs once per bucket range of <= 64 MiB of output --
+    // the digits are recomputed per pass, which is cheap next to the write traffic.
+    // PLK_MSM_SCATTER_PASS_KB: output bytes per pass (0 = always one pass; a small value forces the passes on small inputs: tests)
+    static const long long pass_kb = getenv("PLK_MSM_SCATTER_PASS_KB") ? atoll(getenv("PLK_MSM_SCATTER_PASS_KB")) : -1;
+    const size_t pass_bytes = pass_kb >= 0 ? (size_t)pass_kb << 10 : (size_t)64 << 20;
+    const size_t threshold = pass_kb >= 0 ? pass_bytes : (size_t)96 << 20;
+    const size_t sorted_bytes = (size_t)g.n * g.nwin * 4;
+    unsigned passes = (pass_bytes && sorted_bytes > threshold) ? (unsigned)((sorted_bytes + pass_bytes - 1) / pass_bytes) : 1u;
+    if (passes > 16) passes = 16;
+    for (unsigned ps = 0; ps < passes; ++ps) {
+      const unsigned b_lo = (unsigned)((unsigned long long)g.nb * ps / passes), b_hi = (unsigned)((unsigned long long)g.nb * (ps + 1) / passes);
+      msm_scatter_smem_kernel<C><<<rows, 1024, smem, st>>>(reinterpret_cast<const uint4*>(d_scalars), g, chunk, s->cta_hist.as<unsigned>(),
+                                                           s->offsets.as<unsigned>(), s->sorted.as<unsigned>(), b_lo, b_hi);
+      PLK_LAUNCHED();
+    }
     s->timer.mark(st);
   } else {
     PLK_CUDA(cudaMemsetAsync(s->counts.p, 0, (size_t)g.nb * 4, st));

@@ -4,6 +4,7 @@ re-runs the relevant parity tests in a child process with the knob set.
   PLK_MSM_AFFINE_ROUNDS=2    batched-affine bucket rounds in front of the XYZZ accumulation (csrc/msm_affine.cuh)
   PLK_MSM_MADD_COMPACT=0/2   the other two code-size variants of the mixed addition
   PLK_MSM_BATCH_MERGE=16     batches of short vectors as ONE merged pipeline with a bucket set per vector (default: fork/join)
+  PLK_MSM_SCATTER_PASS_KB=16 the range-partitioned scatter (default only beyond 96 MiB of sorted entries) forced onto small inputs
   PLK_MSM_OVERLAP_PARTS=2/8  the overlapped pipeline: bucket ranges accumulated on their own streams, reduction tails underneath"""
 import os
 import subprocess
@@ -50,3 +51,7 @@ def test_msm_parity_with_overlapped_pipeline(parts, mode):
 @pytest.mark.parametrize("width", ["16", "3"])
 def test_msm_batches_as_merged_pipeline(width):
     run_child({"PLK_MSM_BATCH_MERGE": width}, "batch or commit or ipa", ["test_gpu_parity.py", "test_serde.py", "test_ipa.py"])
+
+
+def test_msm_parity_with_range_partitioned_scatter():
+    run_child({"PLK_MSM_SCATTER_PASS_KB": "16"}, "msm or shard", ["test_gpu_parity.py", "test_gpu_edge.py", "test_gpu_sharded.py"])
