@@ -105,8 +105,12 @@ struct XYZZ {
   // madd with six of its ten products as calls to ONE shared body each (squaring, product): the fully inlined addition is
   // ~2500 instructions = 40 KB per loop iteration of the accumulate kernel, more than the 32 KB instruction cache level that
   // backs the SM (ncu: no_instruction 0.94 stalls per issue); this variant keeps the loop at ~28 KB.  Same values.
-  template <bool ALL = false>
+  // MODE 0: four products inline + six calls; 1: all ten as calls; 2: six inline (also P*PP and X1*PP) + four calls -- the
+  // shipped one.  Measured accumulate times at 2^20 Tweedledee terms: fully inlined 2.519 ms, MODE 0 2.495, MODE 1 2.550,
+  // MODE 2 2.456; seven or eight products inline are back at 2.483-2.486 (the loop outgrows the instruction cache again).
+  template <int MODE = 0>
   PLK_HD static XYZZ madd_compact(const XYZZ& a, const Affine<C>& q) {
+    constexpr bool ALL = MODE == 1, SIX = MODE == 2;
     if (q.is_identity()) return a;
     if (a.is_identity()) return from_affine(q);
     F u2 = ALL ? fp_mul_call<F>(q.x, a.zz) : F::mul(q.x, a.zz);
@@ -118,8 +122,8 @@ struct XYZZ {
       return identity();
     }
     F pp = fp_sqr_call<F>(p);
-    F ppp = fp_mul_call<F>(p, pp);
-    F qq = fp_mul_call<F>(a.x, pp);
+    F ppp = SIX ? F::mul(p, pp) : fp_mul_call<F>(p, pp);
+    F qq = SIX ? F::mul(a.x, pp) : fp_mul_call<F>(a.x, pp);
     XYZZ o;
     o.x = F::sub(F::sub(fp_sqr_call<F>(r), ppp), F::dbl(qq));
     o.y = ALL ? F::sub(fp_mul_call<F>(r, F::sub(qq, o.x)), fp_mul_call<F>(a.y, ppp)) : F::sub(F::mul(r, F::sub(qq, o.x)), F::mul(a.y, ppp));

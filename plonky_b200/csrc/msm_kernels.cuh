@@ -298,7 +298,9 @@ __global__ void __launch_bounds__(kAccThreads, (Fp<typename C::Base>::N <= 8 ? 4
         next = load_affine<C>(table, e & 0x7fffffffu);
       }
       if (negative) p.y = F::neg(p.y);
-      acc = COMPACT == 2 ? XYZZ<C>::template madd_compact<true>(acc, p) : COMPACT == 1 ? XYZZ<C>::template madd_compact<false>(acc, p) : XYZZ<C>::madd(acc, p);
+      acc = COMPACT == 3 ? XYZZ<C>::template madd_compact<2>(acc, p)
+          : COMPACT == 2 ? XYZZ<C>::template madd_compact<1>(acc, p)
+          : COMPACT == 1 ? XYZZ<C>::template madd_compact<0>(acc, p) : XYZZ<C>::madd(acc, p);
     }
     store_xyzz<C>(partials, t, acc);
   }
@@ -835,7 +837,10 @@ void execute_one(plk_msm_table* t, plk_msm_scratch* s, const void* d_scalars, vo
   } else {
     static const int compact = getenv("PLK_MSM_MADD_COMPACT") ? atoi(getenv("PLK_MSM_MADD_COMPACT")) : kMaddCompactDefault;   // see ec.cuh
     auto accumulate = [&](cudaStream_t q, unsigned b_lo, unsigned b_hi, unsigned ablocks) {
-      if (compact == 2)
+      if (compact == 3)
+        msm_accumulate_kernel<C, 3><<<ablocks, kAccThreads, 0, q>>>(t->table.p, s->sorted.as<unsigned>(), s->offsets.as<unsigned>(),
+                                                                    s->task_off.as<unsigned>(), b_lo, b_hi, g.task, s->partials.p);
+      else if (compact == 2)
         msm_accumulate_kernel<C, 2><<<ablocks, kAccThreads, 0, q>>>(t->table.p, s->sorted.as<unsigned>(), s->offsets.as<unsigned>(),
                                                                     s->task_off.as<unsigned>(), b_lo, b_hi, g.task, s->partials.p);
       else if (compact == 1)

@@ -9,7 +9,7 @@ constexpr int kTaskSizeMax = 32;     // S: additions per accumulate task (smalle
 constexpr int kBigBucket = 32;       // buckets with more task partials than this are summed by a whole CTA
 constexpr int kRangeSize = 8;        // buckets per running-sum range
 constexpr int kAccThreads = 128;
-constexpr int kMaddCompactDefault = 1;   // accumulate kernel: 0 fully inlined madd, 1 six products as calls (loop fits the 32 KB I-cache), 2 all ten
+constexpr int kMaddCompactDefault = 3;   // accumulate kernel: 0 fully inlined madd, 1 six products as calls, 2 all ten, 3 four as calls (see ec.cuh)
 constexpr int kQuadThreads = 64;     // CTA size of the quad-cooperative tail kernels (16 quads)
 constexpr int kFinalQuadsMax = 64;   // quads of the single-CTA final reduction
 constexpr int kAffineRoundsHostMax = 3;  // = kAffineRoundsMax of msm_affine.cuh

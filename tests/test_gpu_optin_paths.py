@@ -2,7 +2,7 @@
 re-runs the relevant parity tests in a child process with the knob set.
   PLK_NTT_TMA=1              every qualifying NTT pass through the TMA / Stockham kernel (csrc/ntt_tma.cuh)
   PLK_MSM_AFFINE_ROUNDS=2    batched-affine bucket rounds in front of the XYZZ accumulation (csrc/msm_affine.cuh)
-  PLK_MSM_MADD_COMPACT=0/2   the other two code-size variants of the mixed addition
+  PLK_MSM_MADD_COMPACT=0/1/2 the other code-size variants of the mixed addition (3 = four products as calls is the default)
   PLK_MSM_BATCH_MERGE=16     batches of short vectors as ONE merged pipeline with a bucket set per vector (default: fork/join)
   PLK_MSM_SCATTER_PASS_KB=16 the range-partitioned scatter (default only beyond 96 MiB of sorted entries) forced onto small inputs
   PLK_MSM_OVERLAP_PARTS=2/8  the overlapped pipeline: bucket ranges accumulated on their own streams, reduction tails underneath"""
@@ -38,7 +38,7 @@ def test_msm_parity_with_batched_affine_rounds(rounds):
     run_child({"PLK_MSM_AFFINE_ROUNDS": rounds}, "msm or ipa or summ", ["test_gpu_parity.py", "test_gpu_edge.py", "test_gpu_sharded.py"])
 
 
-@pytest.mark.parametrize("variant", ["0", "2"])
+@pytest.mark.parametrize("variant", ["0", "1", "2"])
 def test_msm_parity_with_other_madd_variants(variant):
     run_child({"PLK_MSM_MADD_COMPACT": variant}, "msm", ["test_gpu_parity.py", "test_gpu_edge.py"])
 
