@@ -106,9 +106,11 @@ void run_ntt(const plk_fft_plan* pl, const void* d_in, size_t n_in, size_t in_st
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
       PLK_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<F, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
       PLK_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<F, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-      PLK_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<F, 2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-      PLK_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<F, 2, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-      PLK_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<F, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+      if constexpr (F::N == 8) {   // compile-time geometry only for the 8-limb fields (the 12-limb instantiations triple that unit's build time)
+        PLK_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<F, 2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+        PLK_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<F, 2, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+        PLK_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<F, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+      }
       if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
   }
@@ -176,10 +178,14 @@ void run_ntt(const plk_fft_plan* pl, const void* d_in, size_t n_in, size_t in_st
     dim3 grid((unsigned)tiles, (unsigned)k);
     // compile-time tile geometry (ntt_kernels.cuh, GEO = 1) whenever the pass has it; PLK_NTT_GEO=0 keeps the generic kernel
     static const int geo = getenv("PLK_NTT_GEO") ? atoi(getenv("PLK_NTT_GEO")) : 1;
-    const bool fixed_geo = radix4 && geo && p.log_t == kGeoLogT && nthreads == kNttThreads;
-    if (fixed_geo && p.r == 8) ntt_pass_kernel<F, 2, 8><<<grid, nthreads, smem, st>>>(p);
-    else if (fixed_geo && p.r == 7) ntt_pass_kernel<F, 2, 7><<<grid, nthreads, smem, st>>>(p);
-    else if (fixed_geo && p.r == 6) ntt_pass_kernel<F, 2, 6><<<grid, nthreads, smem, st>>>(p);
+    const bool fixed_geo = F::N == 8 && radix4 && geo && p.log_t == kGeoLogT && nthreads == kNttThreads && p.r >= kGeoRMin && p.r <= kGeoRMax;
+    if (fixed_geo) {
+      if constexpr (F::N == 8) {
+        if (p.r == 8) ntt_pass_kernel<F, 2, 8><<<grid, nthreads, smem, st>>>(p);
+        else if (p.r == 7) ntt_pass_kernel<F, 2, 7><<<grid, nthreads, smem, st>>>(p);
+        else ntt_pass_kernel<F, 2, 6><<<grid, nthreads, smem, st>>>(p);
+      }
+    }
     else if (radix4) ntt_pass_kernel<F, 2><<<grid, nthreads, smem, st>>>(p);
     else ntt_pass_kernel<F, 3><<<grid, nthreads, smem, st>>>(p);
     PLK_LAUNCHED();
