@@ -183,7 +183,9 @@ __device__ __forceinline__ void ntt_round(const NttPassParams& p, uint4* smem, c
 #pragma unroll
       for (int e = 0; e < (1 << Q); ++e) {
         const size_t orow = bitrev((unsigned)(base_row + e), pr);
-        if (p.tw_all || (orow != 0 && kk != 0)) x[e] = F::mul(x[e], load_fp<F>(p.tw_direct, (orow << p.log_m) + kk));
+        // GEO: multiply unconditionally -- the table holds ONE where the exponent is zero (a product by one returns the same
+        // canonical value), and the skip is a divergent branch around every product for one row in 256
+        if (GEO || p.tw_all || (orow != 0 && kk != 0)) x[e] = F::mul(x[e], load_fp<F>(p.tw_direct, (orow << p.log_m) + kk));
       }
     }
     dit_layers<F, Q, LAYER0>(x, l0, low, wsub);
